@@ -1,0 +1,204 @@
+"""ctypes binding of include/pm.h (the C-ABI of libpm.so).
+
+Host-side mirror used by tests/ and bench.py.  It binds exactly the symbols
+include/pm.h declares and nothing else; there is no fallback: if libpm.so is
+missing or a symbol is absent, import-time loading raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libpm.so")
+
+PM_OK = 0
+CASE_CAVITY, CASE_CHANNEL, CASE_STEP = 0, 1, 2
+PPE_JACOBI, PPE_SOR_RB, PPE_SOR_LEX = 0, 1, 2
+F_U, F_V, F_P, F_USTAR, F_VSTAR, F_F = range(6)
+PATH_AUTO, PATH_SIMPLE, PATH_TILED = 0, 1, 2
+
+
+class PmConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("case_id", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32),
+        ("dx", C.c_double), ("dy", C.c_double), ("nu", C.c_double), ("dt", C.c_double),
+        ("u_ref", C.c_double), ("rho", C.c_double), ("omega", C.c_double),
+        ("tol_factor", C.c_double), ("abs_tol", C.c_double),
+        ("max_iters", C.c_int32), ("ppe_method", C.c_int32), ("exact_arith", C.c_int32),
+        ("sweeps_per_pass", C.c_int32), ("kernel_path", C.c_int32),
+        ("step_i_location", C.c_int32), ("inlet_j_max", C.c_int32),
+        ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("poll_chunk", C.c_int32),
+        ("nccl_id", C.c_uint8 * 128),
+        ("lx", C.c_double), ("ly", C.c_double), ("re", C.c_double), ("cfl", C.c_double), ("final_time", C.c_double),
+        ("total_steps", C.c_int32), ("print_interval", C.c_int32), ("save_interval", C.c_int32), ("reserved_", C.c_int32),
+    ]
+
+    def copy(self):
+        c = PmConfig()
+        C.memmove(C.byref(c), C.byref(self), C.sizeof(PmConfig))
+        return c
+
+
+class PmPpeResult(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("hit_cap", C.c_int32), ("residual", C.c_double),
+                ("tolerance", C.c_double), ("max_source", C.c_double)]
+
+
+class PmTiming(C.Structure):
+    _fields_ = [("ppe_ms", C.c_double), ("other_ms", C.c_double),
+                ("kernel_launches", C.c_int64), ("ppe_passes", C.c_int64)]
+
+
+def field_shape(field, nx, ny):
+    """Reference array shapes (cavity-01.cpp:433-441)."""
+    if field in (F_U, F_USTAR):
+        return (ny + 2, nx + 1)
+    if field in (F_V, F_VSTAR):
+        return (ny + 1, nx + 2)
+    return (ny + 2, nx + 2)
+
+
+EXPORTS = [
+    "pm_config_init", "pm_slab_range", "pm_create", "pm_destroy", "pm_last_error", "pm_status_string",
+    "pm_abi_version", "pm_nccl_unique_id", "pm_upload", "pm_download", "pm_upload_mask", "pm_download_mask",
+    "pm_fill_random", "pm_fill_zero", "pm_apply_bc", "pm_predict", "pm_source", "pm_ppe_solve", "pm_correct",
+    "pm_step", "pm_diagnostics", "pm_sync", "pm_get_timing",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libpm.so (built by __graft_entry__.build()); raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name in EXPORTS:
+        getattr(L, name)  # AttributeError if the library does not export what pm.h declares
+    vp, dp = C.c_void_p, C.POINTER(C.c_double)
+    L.pm_config_init.argtypes = [C.POINTER(PmConfig), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+    L.pm_slab_range.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.pm_create.argtypes = [C.POINTER(PmConfig), C.POINTER(vp)]
+    L.pm_destroy.argtypes = [vp]
+    L.pm_last_error.argtypes = [vp]; L.pm_last_error.restype = C.c_char_p
+    L.pm_status_string.argtypes = [C.c_int]; L.pm_status_string.restype = C.c_char_p
+    L.pm_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    L.pm_upload.argtypes = [vp, C.c_int, dp, C.c_size_t]
+    L.pm_download.argtypes = [vp, C.c_int, dp, C.c_size_t]
+    L.pm_upload_mask.argtypes = [vp, C.POINTER(C.c_uint8), C.c_size_t]
+    L.pm_download_mask.argtypes = [vp, C.POINTER(C.c_uint8), C.c_size_t]
+    L.pm_fill_random.argtypes = [vp, C.c_uint64]
+    L.pm_fill_zero.argtypes = [vp]
+    L.pm_apply_bc.argtypes = [vp, C.c_int]
+    for n in ("pm_predict", "pm_source", "pm_correct", "pm_sync"):
+        getattr(L, n).argtypes = [vp]
+    L.pm_ppe_solve.argtypes = [vp, C.POINTER(PmPpeResult)]
+    L.pm_step.argtypes = [vp, C.c_int, C.POINTER(PmPpeResult)]
+    L.pm_diagnostics.argtypes = [vp, dp, dp]
+    L.pm_get_timing.argtypes = [vp, C.POINTER(PmTiming)]
+    _lib = L
+    return L
+
+
+class PmError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"pm status {status}: {msg}")
+        self.status = status
+
+
+def config_init(case_id, nx=0, ny=0, re=0.0, dt=0.0):
+    cfg = PmConfig()
+    st = lib().pm_config_init(C.byref(cfg), case_id, nx, ny, re, dt)
+    if st != PM_OK:
+        raise PmError(st, lib().pm_status_string(st).decode())
+    return cfg
+
+
+class Solver:
+    """Thin object wrapper; method names follow the reference's member functions."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        st = lib().pm_create(C.byref(cfg), C.byref(self._h))
+        if st != PM_OK:
+            raise PmError(st, (lib().pm_last_error(None) or b"").decode())
+
+    def _ck(self, st):
+        if st != PM_OK:
+            raise PmError(st, (lib().pm_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if self._h:
+            lib().pm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, field, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        assert a.shape == field_shape(field, self.cfg.nx, self.cfg.ny), (a.shape, field)
+        self._ck(lib().pm_upload(self._h, field, a.ctypes.data_as(C.POINTER(C.c_double)), a.size))
+
+    def download(self, field, out=None):
+        if out is None:
+            out = np.empty(field_shape(field, self.cfg.nx, self.cfg.ny), dtype=np.float64)
+        self._ck(lib().pm_download(self._h, field, out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
+        return out
+
+    def upload_mask(self, m):
+        a = np.ascontiguousarray(m, dtype=np.uint8)
+        self._ck(lib().pm_upload_mask(self._h, a.ctypes.data_as(C.POINTER(C.c_uint8)), a.size))
+
+    def download_mask(self):
+        out = np.empty((self.cfg.ny + 2, self.cfg.nx + 2), dtype=np.uint8)
+        self._ck(lib().pm_download_mask(self._h, out.ctypes.data_as(C.POINTER(C.c_uint8)), out.size))
+        return out
+
+    def fill_random(self, seed):
+        self._ck(lib().pm_fill_random(self._h, seed))
+
+    def fill_zero(self):
+        self._ck(lib().pm_fill_zero(self._h))
+
+    def apply_bc(self, which=0):
+        self._ck(lib().pm_apply_bc(self._h, which))
+
+    def predict(self):
+        self._ck(lib().pm_predict(self._h))
+
+    def source(self):
+        self._ck(lib().pm_source(self._h))
+
+    def ppe_solve(self):
+        r = PmPpeResult()
+        self._ck(lib().pm_ppe_solve(self._h, C.byref(r)))
+        return r
+
+    def correct(self):
+        self._ck(lib().pm_correct(self._h))
+
+    def step(self, n=1):
+        r = PmPpeResult()
+        self._ck(lib().pm_step(self._h, n, C.byref(r)))
+        return r
+
+    def diagnostics(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(lib().pm_diagnostics(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def sync(self):
+        self._ck(lib().pm_sync(self._h))
+
+    def timing(self):
+        t = PmTiming()
+        self._ck(lib().pm_get_timing(self._h, C.byref(t)))
+        return t

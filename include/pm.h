@@ -1,0 +1,182 @@
+/*
+ * pm.h — C-ABI of the B200-native projection-method time step.
+ *
+ * Drop-in boundary for the hot path of tjjones6/Computational-Fluid-Dynamics.
+ * The reference has no plugin/FFI seam: each solver's run() calls private
+ * members that mutate the solver's own fields
+ *   cavity-01.cpp:387-390   (BC, predictor, PPE, correction)
+ *   channel-01.cpp:368-375  (predictor, BC(u*,v*), source, PPE, correction, BC)
+ *   backwards_step-01.cpp:412-419 (same as channel, with the is_fluid mask)
+ * This header is the seam a maintainer would bind instead of those calls
+ * (see INTEGRATION.md).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Array shapes at the boundary are the reference's (dense, row-major,
+ * field[j][i], j = row):
+ *   p, f            : (ny+2) x (nx+2)   cavity-01.cpp:433-435
+ *   u, u*           : (ny+2) x (nx+1)   cavity-01.cpp:436-437
+ *   v, v*           : (ny+1) x (nx+2)   cavity-01.cpp:439-440
+ *   mask (is_fluid) : (ny+2) x (nx+2) bytes, backwards_step-01.cpp:480-483
+ *
+ * Every entry point returns a pm_status; 0 is success.  No exception crosses
+ * the boundary.  A handle is driven by one host thread; independent handles
+ * may coexist.  There is no CPU fallback: without a usable CUDA device
+ * pm_create fails with PM_ERR_CUDA.
+ */
+#ifndef PM_H_
+#define PM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_ABI_VERSION 1
+
+typedef enum pm_status {
+  PM_OK = 0,
+  PM_ERR_INVALID_ARGUMENT = 1, /* std::invalid_argument in the reference (create_field, cavity-01.cpp:57-59) */
+  PM_ERR_RUNTIME = 2,          /* std::runtime_error (dt <= 0 cavity-01.cpp:423-425; step outside domain backwards_step-01.cpp:459-461) */
+  PM_ERR_CUDA = 3,             /* CUDA runtime/driver failure, or no device */
+  PM_ERR_NCCL = 4,             /* NCCL failure or libnccl not loadable */
+  PM_ERR_UNSUPPORTED = 5       /* combination not implemented (e.g. sor-lex on >1 rank) */
+} pm_status;
+
+/* Which reference solver's semantics the handle reproduces. */
+typedef enum pm_case {
+  PM_CASE_CAVITY = 0,  /* cavity-01.cpp          */
+  PM_CASE_CHANNEL = 1, /* channel-01.cpp         */
+  PM_CASE_STEP = 2     /* backwards_step-01.cpp  */
+} pm_case;
+
+/* Ordering of the pressure-Poisson sweep.  The reference only has the
+ * lexicographic one (cavity-01.cpp:640-656, channel-01.cpp:657-668). */
+typedef enum pm_ppe_method {
+  PM_PPE_JACOBI = 0,  /* deterministic verification mode */
+  PM_PPE_SOR_RB = 1,  /* production: red-black SOR        */
+  PM_PPE_SOR_LEX = 2  /* reference ordering, wavefront-parallel, single rank only */
+} pm_ppe_method;
+
+typedef enum pm_field {
+  PM_FIELD_U = 0,      /* u_corrected */
+  PM_FIELD_V = 1,      /* v_corrected */
+  PM_FIELD_P = 2,      /* pressure    */
+  PM_FIELD_USTAR = 3,  /* u_tentative */
+  PM_FIELD_VSTAR = 4,  /* v_tentative */
+  PM_FIELD_F = 5,      /* source_term */
+  PM_FIELD_COUNT = 6
+} pm_field;
+
+typedef enum pm_kernel_path {
+  PM_PATH_AUTO = 0,
+  PM_PATH_SIMPLE = 1, /* one global-memory pass per colour + separate residual pass */
+  PM_PATH_TILED = 2   /* TMA-staged shared-memory tiles, fused residual, temporal blocking */
+} pm_kernel_path;
+
+typedef struct pm_config {
+  uint32_t struct_size; /* sizeof(pm_config); checked by pm_create */
+  int32_t case_id;      /* pm_case */
+  int32_t nx, ny;       /* GLOBAL interior cell counts */
+  double dx, dy;        /* cavity: dx == dy == grid_spacing */
+  double nu;            /* kinematic viscosity */
+  double dt;            /* time step */
+  double u_ref;         /* lid velocity (cavity) / inlet velocity (channel, step) */
+  double rho;           /* density */
+  double omega;         /* relaxation factor */
+  double tol_factor;    /* cavity 1e-9 (cavity-01.cpp:317); channel/step 1e-7 */
+  double abs_tol;       /* channel/step 1e-10 (channel-01.cpp:297); unused by cavity */
+  int32_t max_iters;    /* 10000 in the reference */
+  int32_t ppe_method;   /* pm_ppe_method */
+  int32_t exact_arith;  /* 1: no FMA contraction, IEEE divides, serial-order mean: bit-identical to the oracle */
+  int32_t sweeps_per_pass; /* temporal-blocking depth of the tiled path; 0 = auto */
+  int32_t kernel_path;  /* pm_kernel_path */
+  int32_t step_i_location; /* step: last solid column  (backwards_step-01.cpp:386) */
+  int32_t inlet_j_max;     /* step: last inlet row     (backwards_step-01.cpp:493) */
+  int32_t device;       /* CUDA device ordinal; -1 = current device */
+  int32_t rank, nranks; /* slab decomposition in j; single GPU: 0, 1 */
+  int32_t poll_chunk;   /* PPE passes enqueued between host polls of the device-side stop flag; 0 = auto */
+  uint8_t nccl_id[128]; /* ncclUniqueId shared by all ranks (pm_nccl_unique_id on rank 0); ignored when nranks == 1 */
+  /* Informational: filled by pm_config_init for the drivers, not read by the kernels. */
+  double lx, ly, re, cfl, final_time;
+  int32_t total_steps, print_interval, save_interval;
+  int32_t reserved_;
+} pm_config;
+
+typedef struct pm_ppe_result {
+  int32_t iterations;  /* == reference's iteration_count */
+  int32_t hit_cap;     /* iterations >= max_iters: the reference prints a warning (cavity-01.cpp:681-684) */
+  double residual;     /* final max|r| (infinity norm) */
+  double tolerance;    /* the tolerance the loop used */
+  double max_source;   /* max|f| seen by the tolerance rule */
+} pm_ppe_result;
+
+typedef struct pm_solver pm_solver;
+
+/* ---- configuration (host only; a1/a2 of SURVEY §8a) -------------------- */
+
+/* Fill *cfg with the reference's compiled-in constants for `case_id`
+ * (cavity-01.cpp:309-320,356-363; channel-01.cpp:287-300,337-344;
+ * backwards_step-01.cpp:319-334,378-387), overriding Re, nx, ny, dt when the
+ * argument is > 0 (the README's --Re --Nx --Ny --dt).  dt <= 0 keeps the
+ * reference's CFL rule.  Derives nu, dx, dy, omega, dt, total_steps and the
+ * step geometry with the reference's own expression trees. */
+int pm_config_init(pm_config* cfg, int case_id, int nx, int ny, double re, double dt);
+
+/* Rows of the global grid owned by `rank`: interior rows j0+1 .. j0+ny_local. */
+int pm_slab_range(int ny, int nranks, int rank, int* j0, int* ny_local);
+
+/* ---- lifetime ---------------------------------------------------------- */
+int pm_create(const pm_config* cfg, pm_solver** out);
+int pm_destroy(pm_solver* s);
+const char* pm_last_error(const pm_solver* s); /* s may be NULL: error of the last failed pm_create on this thread */
+const char* pm_status_string(int status);
+int pm_abi_version(void);
+
+/* 128-byte ncclUniqueId for pm_config.nccl_id (call on one rank, broadcast to the others). */
+int pm_nccl_unique_id(uint8_t out[128]);
+
+/* ---- data movement (reference array shapes, GLOBAL arrays) ------------- */
+/* `count` must equal the element count of the global field.  With nranks > 1
+ * each rank copies only its own slab (plus halo rows) from/to the global array. */
+int pm_upload(pm_solver* s, int field, const double* host, size_t count);
+int pm_download(pm_solver* s, int field, double* host, size_t count);
+int pm_upload_mask(pm_solver* s, const uint8_t* is_fluid, size_t count);   /* step only; default is the reference rectangle */
+int pm_download_mask(pm_solver* s, uint8_t* is_fluid, size_t count);
+/* Synthetic state generated on the device: value(field, j, i) = U(-1,1) from
+ * splitmix64(seed, field, flat reference index).  Same generator in oracle/. */
+int pm_fill_random(pm_solver* s, uint64_t seed);
+int pm_fill_zero(pm_solver* s);
+
+/* ---- phases (one per reference member function) ------------------------ */
+/* which = 0: (u,v)  [applyBoundaryConditions]; 1: (u*,v*) [channel-01.cpp:369] */
+int pm_apply_bc(pm_solver* s, int which);
+int pm_predict(pm_solver* s);                      /* computeTentativeVelocities */
+int pm_source(pm_solver* s);                       /* source term (+ mean removal for channel/step) */
+int pm_ppe_solve(pm_solver* s, pm_ppe_result* r);  /* solverPressurePoisson (cavity: without the source loop, which pm_source does) */
+int pm_correct(pm_solver* s);                      /* applyPressureCorrection */
+
+/* nsteps whole projection steps in the case's own call order
+ * (cavity-01.cpp:387-390 / channel-01.cpp:368-375).  *last may be NULL. */
+int pm_step(pm_solver* s, int nsteps, pm_ppe_result* last);
+
+/* max|div u| over (fluid) cells and mean kinetic energy of the cell-centred
+ * velocity (logStatistics, cavity-01.cpp:741-766). */
+int pm_diagnostics(pm_solver* s, double* max_div, double* avg_ke);
+
+/* Block until all work queued on the handle has finished. */
+int pm_sync(pm_solver* s);
+
+/* ---- measurement helpers ------------------------------------------------ */
+typedef struct pm_timing {
+  double ppe_ms;        /* device time in PPE kernels during the last pm_step/pm_ppe_solve */
+  double other_ms;      /* device time of the other phases of the last pm_step */
+  int64_t kernel_launches; /* kernels launched by this handle since creation */
+  int64_t ppe_passes;   /* PPE kernel passes since creation */
+} pm_timing;
+int pm_get_timing(pm_solver* s, pm_timing* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PM_H_ */
