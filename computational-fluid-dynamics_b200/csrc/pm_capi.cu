@@ -1,0 +1,767 @@
+// pm_capi.cu — host side of libpm.so: the handle, the HBM layout, the per-phase launch sequences
+// and the C-ABI of include/pm.h.  Host code is C++17; every device entry is a hand-written
+// sm_100a kernel from pm_kernels_*.cuh.  There is no CPU fallback anywhere in this file.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/pm.h"
+#include "pm_common.cuh"
+#include "pm_kernels_simple.cuh"
+#include "pm_kernels_tiled.cuh"
+#include "pm_nccl.hpp"
+
+// ---------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------
+enum { PL_U = 0, PL_V, PL_US, PL_VS, PL_F, PL_P0, PL_P1, PL_COUNT };
+
+struct pm_solver {
+  pm_config cfg{};
+  KP kp{};
+  int device = 0;
+  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_halo = nullptr, ev_edge = nullptr;
+  size_t plane = 0;        // doubles per plane
+  int rows_alloc = 0;
+  double* base = nullptr;  // PL_COUNT planes
+  double* pl[PL_COUNT] = {};
+  int p_cur = PL_P0;       // plane holding the current pressure
+  uint8_t* mask = nullptr; // same geometry, bytes
+  PpeState* d_state = nullptr;
+  unsigned long long* d_res = nullptr;  // max_iters + 2 entries
+  double* d_partial = nullptr;
+  int n_partial = 0;
+  PpeState* h_state = nullptr;  // pinned
+  unsigned long long* h_res = nullptr;  // pinned, max_iters + 2
+  bool f_max_valid = false;
+  int last_iters = 0;
+  bool use_tiled = false;
+  int sweeps = 1;
+  TiledPlan tiled{};
+  PmNccl nccl{};
+  pm_timing timing{};
+  std::string err;
+};
+
+static thread_local std::string g_create_error;
+
+static int fail(pm_solver* s, int status, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (s) s->err = buf; else g_create_error = buf;
+  return status;
+}
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(s, PM_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CKL(s_)                                                                                           \
+  do {                                                                                                    \
+    cudaError_t e_ = cudaGetLastError();                                                                  \
+    if (e_ != cudaSuccess) return fail(s_, PM_ERR_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    (s_)->timing.kernel_launches++;                                                                       \
+  } while (0)
+#define PMTRY(expr)            \
+  do {                         \
+    int st_ = (expr);          \
+    if (st_ != PM_OK) return st_; \
+  } while (0)
+
+static inline dim3 cell_block() { return dim3(PM_BX, PM_BY); }
+static inline dim3 cell_grid(const KP& k) { return dim3((k.nx + PM_BX - 1) / PM_BX, (k.nyl + PM_BY - 1) / PM_BY); }
+static inline dim3 half_grid(const KP& k) { return dim3(((k.nx + 1) / 2 + PM_BX - 1) / PM_BX, (k.nyl + PM_BY - 1) / PM_BY); }
+
+static void field_dims(const pm_solver* s, int field, int* rows, int* cols) {
+  const int nx = s->cfg.nx, ny = s->cfg.ny;
+  switch (field) {
+    case PM_FIELD_U: case PM_FIELD_USTAR: *rows = ny + 2; *cols = nx + 1; break;
+    case PM_FIELD_V: case PM_FIELD_VSTAR: *rows = ny + 1; *cols = nx + 2; break;
+    default: *rows = ny + 2; *cols = nx + 2; break;
+  }
+}
+static double* field_plane(pm_solver* s, int field) {
+  switch (field) {
+    case PM_FIELD_U: return s->pl[PL_U];
+    case PM_FIELD_V: return s->pl[PL_V];
+    case PM_FIELD_P: return s->pl[s->p_cur];
+    case PM_FIELD_USTAR: return s->pl[PL_US];
+    case PM_FIELD_VSTAR: return s->pl[PL_VS];
+    case PM_FIELD_F: return s->pl[PL_F];
+  }
+  return nullptr;
+}
+
+// ---------------------------------------------------------------------------
+// misc exported helpers
+// ---------------------------------------------------------------------------
+extern "C" int pm_abi_version(void) { return PM_ABI_VERSION; }
+
+extern "C" const char* pm_status_string(int status) {
+  switch (status) {
+    case PM_OK: return "ok";
+    case PM_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case PM_ERR_RUNTIME: return "runtime error";
+    case PM_ERR_CUDA: return "CUDA error";
+    case PM_ERR_NCCL: return "NCCL error";
+    case PM_ERR_UNSUPPORTED: return "unsupported";
+  }
+  return "unknown status";
+}
+extern "C" const char* pm_last_error(const pm_solver* s) { return s ? s->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int pm_nccl_unique_id(uint8_t out[128]) {
+  std::string e;
+  if (!pm_nccl_get_unique_id(out, &e)) return fail(nullptr, PM_ERR_NCCL, "%s", e.c_str());
+  return PM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// create / destroy
+// ---------------------------------------------------------------------------
+static void fill_kp(pm_solver* s, int j0, int nyl) {
+  const pm_config& c = s->cfg;
+  KP& k = s->kp;
+  std::memset(&k, 0, sizeof k);
+  k.nx = c.nx; k.ny = c.ny; k.nyl = nyl; k.j0 = j0;
+  // pitch: PM_OFFC left pad + nx+2 columns + right pad for tile halos, rounded to 16 doubles (128 B)
+  k.pitch = ((PM_OFFC + c.nx + 2 + PM_PADR + 15) / 16) * 16;
+  k.padr = PM_PADR;
+  k.case_id = c.case_id;
+  k.has_mask = c.case_id == PM_CASE_STEP;
+  k.first_rank = c.rank == 0;
+  k.last_rank = c.rank == c.nranks - 1;
+  k.inlet_j_max = c.inlet_j_max;
+  // the reference's per-call locals, same expression trees (cavity-01.cpp:549-550,613-615; channel-01.cpp:547-550,638-640)
+  k.idx = 1.0 / c.dx; k.idy = 1.0 / c.dy;
+  k.idx2 = 1.0 / (c.dx * c.dx); k.idy2 = 1.0 / (c.dy * c.dy);
+  k.hh = c.dx * c.dx;
+  k.nu = c.nu; k.dt = c.dt; k.uref = c.u_ref; k.two_uref = 2.0 * c.u_ref;
+  k.omega = c.omega; k.om1 = 1.0 - c.omega;
+  for (int n = 1; n <= 4; ++n) k.wnc[n] = c.omega / n;
+  k.wnc[0] = 0.0;
+  k.denom = 2.0 * (k.idx2 + k.idy2);
+  k.rdenom = 1.0 / k.denom;
+  if (c.case_id == PM_CASE_CAVITY) {
+    const double dti = 1.0 / c.dt;
+    k.src_coef = dti * c.rho;               // time_step_inv * density, cavity-01.cpp:624
+    const double dt_over_h = c.dt / c.dx;   // :696
+    k.cu = dt_over_h * c.rho; k.cv = k.cu;  // :701,:708
+  } else {
+    k.src_coef = c.rho / c.dt;              // channel-01.cpp:610
+    k.cu = c.dt / (c.rho * c.dx);           // :697
+    k.cv = c.dt / (c.rho * c.dy);           // :701
+  }
+  k.tol_factor = c.tol_factor; k.abs_tol = c.abs_tol;
+  k.max_iters = c.max_iters;
+  k.fluid_count_global = c.nx * c.ny;
+}
+
+static int upload_mask_rows(pm_solver* s, const uint8_t* global_mask) {
+  const KP& k = s->kp;
+  const int cols = k.nx + 2;
+  int cnt = 0;
+  for (int j = 1; j <= k.ny; ++j)
+    for (int i = 1; i <= k.nx; ++i) cnt += global_mask[size_t(j) * cols + i] ? 1 : 0;
+  s->kp.fluid_count_global = cnt;
+  CK(cudaMemsetAsync(s->mask, 0, s->plane, s->stream));
+  // local rows 0..nyl+1 <- global rows j0..j0+nyl+1
+  CK(cudaMemcpy2DAsync(s->mask + pm_idx(k, 0, 0), size_t(k.pitch), global_mask + size_t(k.j0) * cols, size_t(cols),
+                       size_t(cols), size_t(k.nyl + 2), cudaMemcpyHostToDevice, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return PM_OK;
+}
+
+static int destroy_impl(pm_solver* s) {
+  if (!s) return PM_OK;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  pm_nccl_destroy(&s->nccl);
+  tiled_destroy(&s->tiled);
+  if (s->base) cudaFree(s->base);
+  if (s->mask) cudaFree(s->mask);
+  if (s->d_state) cudaFree(s->d_state);
+  if (s->d_res) cudaFree(s->d_res);
+  if (s->d_partial) cudaFree(s->d_partial);
+  if (s->h_state) cudaFreeHost(s->h_state);
+  if (s->h_res) cudaFreeHost(s->h_res);
+  for (cudaEvent_t e : {s->ev_a, s->ev_b, s->ev_t0, s->ev_t1, s->ev_halo, s->ev_edge})
+    if (e) cudaEventDestroy(e);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+  delete s;
+  return PM_OK;
+}
+
+static int create_impl(pm_solver* s, const pm_config* cfg) {
+  s->cfg = *cfg;
+  const pm_config& c = s->cfg;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(s, PM_ERR_CUDA, "no CUDA device: libpm has no CPU path");
+  if (c.device >= 0) {
+    if (c.device >= ndev) return fail(s, PM_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", c.device, ndev);
+    s->device = c.device;
+  } else {
+    CK(cudaGetDevice(&s->device));
+  }
+  CK(cudaSetDevice(s->device));
+
+  int j0 = 0, nyl = c.ny;
+  if (pm_slab_range(c.ny, c.nranks, c.rank, &j0, &nyl) != PM_OK)
+    return fail(s, PM_ERR_INVALID_ARGUMENT, "bad slab decomposition: ny=%d nranks=%d rank=%d", c.ny, c.nranks, c.rank);
+  fill_kp(s, j0, nyl);
+  const KP& k = s->kp;
+
+  CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&s->ev_a, &s->ev_b, &s->ev_t0, &s->ev_t1}) CK(cudaEventCreate(e));
+  for (cudaEvent_t* e : {&s->ev_halo, &s->ev_edge}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+
+  s->rows_alloc = nyl + 2 + 2 * k.padr;
+  s->plane = size_t(k.pitch) * size_t(s->rows_alloc);
+  CK(cudaMalloc(&s->base, s->plane * PL_COUNT * sizeof(double)));
+  CK(cudaMemsetAsync(s->base, 0, s->plane * PL_COUNT * sizeof(double), s->stream));
+  for (int q = 0; q < PL_COUNT; ++q) s->pl[q] = s->base + s->plane * q;
+  CK(cudaMalloc(&s->mask, s->plane));
+  CK(cudaMemsetAsync(s->mask, 0, s->plane, s->stream));
+  CK(cudaMalloc(&s->d_state, sizeof(PpeState)));
+  CK(cudaMemsetAsync(s->d_state, 0, sizeof(PpeState), s->stream));
+  CK(cudaMalloc(&s->d_res, size_t(c.max_iters + 2) * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(s->d_res, 0, size_t(c.max_iters + 2) * sizeof(unsigned long long), s->stream));
+  const dim3 g = cell_grid(k);
+  s->n_partial = int(g.x * g.y);
+  CK(cudaMalloc(&s->d_partial, size_t(s->n_partial) * sizeof(double)));
+  CK(cudaMallocHost(&s->h_state, sizeof(PpeState)));
+  CK(cudaMallocHost(&s->h_res, size_t(c.max_iters + 2) * sizeof(unsigned long long)));
+
+  // is_fluid: interior true; step: the reference rectangle (backwards_step-01.cpp:500-520)
+  {
+    std::vector<uint8_t> m(size_t(c.ny + 2) * (c.nx + 2), 0);
+    for (int j = 1; j <= c.ny; ++j)
+      for (int i = 1; i <= c.nx; ++i)
+        m[size_t(j) * (c.nx + 2) + i] =
+            (c.case_id != PM_CASE_STEP) || (i > c.step_i_location) || (j <= c.inlet_j_max) ? 1 : 0;
+    PMTRY(upload_mask_rows(s, m.data()));
+  }
+
+  // kernel path
+  const bool tiled_ok = tiled_supported(c, k);
+  if (c.kernel_path == PM_PATH_TILED && !tiled_ok)
+    return fail(s, PM_ERR_UNSUPPORTED, "tiled path supports unmasked jacobi / sor-rb only");
+  s->use_tiled = tiled_ok && (c.kernel_path == PM_PATH_TILED ||
+                              (c.kernel_path == PM_PATH_AUTO && size_t(c.nx) * size_t(nyl) >= (size_t(1) << 18)));
+  if (s->use_tiled) {
+    std::string e;
+    if (!tiled_create(&s->tiled, c, k, s->pl[PL_P0], s->pl[PL_P1], s->pl[PL_F], s->rows_alloc, &e))
+      return fail(s, PM_ERR_CUDA, "tiled path setup: %s", e.c_str());
+    s->sweeps = s->tiled.sweeps;
+  }
+
+  if (c.nranks > 1) {
+    if (c.ppe_method == PM_PPE_SOR_LEX)
+      return fail(s, PM_ERR_UNSUPPORTED, "sor-lex does not shard (SURVEY 8e); use jacobi or sor-rb with nranks > 1");
+    std::string e;
+    if (!pm_nccl_init(&s->nccl, c.nccl_id, c.nranks, c.rank, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
+  }
+  CK(cudaStreamSynchronize(s->stream));
+  return PM_OK;
+}
+
+extern "C" int pm_create(const pm_config* cfg, pm_solver** out) {
+  if (!cfg || !out) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  if (cfg->struct_size != sizeof(pm_config))
+    return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "pm_config.struct_size %u != %zu (ABI mismatch)", cfg->struct_size, sizeof(pm_config));
+  // create_field, cavity-01.cpp:57-59
+  if (cfg->nx <= 0 || cfg->ny <= 0) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "Field dimensions must be positive");
+  if (cfg->case_id < PM_CASE_CAVITY || cfg->case_id > PM_CASE_STEP) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "unknown case %d", cfg->case_id);
+  if (cfg->ppe_method < PM_PPE_JACOBI || cfg->ppe_method > PM_PPE_SOR_LEX) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "unknown ppe method %d", cfg->ppe_method);
+  if (cfg->nx < 2 || cfg->ny < 2) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "grid must be at least 2x2");
+  if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "bad rank %d of %d", cfg->rank, cfg->nranks);
+  if (cfg->max_iters < 0 || cfg->max_iters > (1 << 24)) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "max_iters out of range");
+  // validateParameters, cavity-01.cpp:423-425
+  if (!(cfg->dt > 0)) return fail(nullptr, PM_ERR_RUNTIME, "Computed time step is non-positive. Check physical parameters!");
+  if (!(cfg->dx > 0) || !(cfg->dy > 0)) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "grid spacing must be positive");
+  // backwards_step-01.cpp:459-461
+  if (cfg->case_id == PM_CASE_STEP && (cfg->step_i_location <= 0 || cfg->step_i_location >= cfg->nx))
+    return fail(nullptr, PM_ERR_RUNTIME, "Step location is outside computational domain!");
+  pm_solver* s = new (std::nothrow) pm_solver();
+  if (!s) return fail(nullptr, PM_ERR_RUNTIME, "out of host memory");
+  const int st = create_impl(s, cfg);
+  if (st != PM_OK) {
+    g_create_error = s->err;
+    destroy_impl(s);
+    return st;
+  }
+  *out = s;
+  return PM_OK;
+}
+extern "C" int pm_destroy(pm_solver* s) { return destroy_impl(s); }
+
+extern "C" int pm_sync(pm_solver* s) {
+  if (!s) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  CK(cudaStreamSynchronize(s->stream));
+  return PM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// data movement
+// ---------------------------------------------------------------------------
+// Local storage rows jl_a..jl_b of a field correspond to global rows j0+jl.
+static void local_row_span(const pm_solver* s, int rows_global, bool with_halo, int* ja, int* jb) {
+  const KP& k = s->kp;
+  int a = with_halo ? 0 : (k.first_rank ? 0 : 1);
+  int b = with_halo ? k.nyl + 1 : (k.last_rank ? k.nyl + 1 : k.nyl);
+  b = std::min(b, rows_global - 1 - k.j0);
+  *ja = a; *jb = b;
+}
+
+extern "C" int pm_upload(pm_solver* s, int field, const double* host, size_t count) {
+  if (!s || !host) return PM_ERR_INVALID_ARGUMENT;
+  int rows, cols;
+  field_dims(s, field, &rows, &cols);
+  double* dst = field_plane(s, field);
+  if (!dst) return fail(s, PM_ERR_INVALID_ARGUMENT, "unknown field %d", field);
+  if (count != size_t(rows) * cols) return fail(s, PM_ERR_INVALID_ARGUMENT, "field %d expects %zu elements, got %zu", field, size_t(rows) * cols, count);
+  CK(cudaSetDevice(s->device));
+  int ja, jb;
+  local_row_span(s, rows, true, &ja, &jb);
+  const KP& k = s->kp;
+  CK(cudaMemcpy2DAsync(dst + pm_idx(k, ja, 0), size_t(k.pitch) * 8, host + size_t(k.j0 + ja) * cols, size_t(cols) * 8,
+                       size_t(cols) * 8, size_t(jb - ja + 1), cudaMemcpyHostToDevice, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  if (field == PM_FIELD_F) s->f_max_valid = false;
+  return PM_OK;
+}
+extern "C" int pm_download(pm_solver* s, int field, double* host, size_t count) {
+  if (!s || !host) return PM_ERR_INVALID_ARGUMENT;
+  int rows, cols;
+  field_dims(s, field, &rows, &cols);
+  double* src = field_plane(s, field);
+  if (!src) return fail(s, PM_ERR_INVALID_ARGUMENT, "unknown field %d", field);
+  if (count != size_t(rows) * cols) return fail(s, PM_ERR_INVALID_ARGUMENT, "field %d expects %zu elements, got %zu", field, size_t(rows) * cols, count);
+  CK(cudaSetDevice(s->device));
+  int ja, jb;
+  local_row_span(s, rows, false, &ja, &jb);
+  const KP& k = s->kp;
+  if (jb >= ja)
+    CK(cudaMemcpy2DAsync(host + size_t(k.j0 + ja) * cols, size_t(cols) * 8, src + pm_idx(k, ja, 0), size_t(k.pitch) * 8,
+                         size_t(cols) * 8, size_t(jb - ja + 1), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return PM_OK;
+}
+extern "C" int pm_slab_rows(pm_solver* s, int field, int* first_global_row, int* nrows, int* ncols) {
+  if (!s || field < 0 || field >= PM_FIELD_COUNT) return PM_ERR_INVALID_ARGUMENT;
+  int rows, cols, ja, jb;
+  field_dims(s, field, &rows, &cols);
+  local_row_span(s, rows, true, &ja, &jb);
+  if (first_global_row) *first_global_row = s->kp.j0 + ja;
+  if (nrows) *nrows = jb - ja + 1;
+  if (ncols) *ncols = cols;
+  return PM_OK;
+}
+static int slab_copy(pm_solver* s, int field, double* host, size_t count, bool to_device) {
+  if (!s || !host) return PM_ERR_INVALID_ARGUMENT;
+  int rows, cols, ja, jb;
+  field_dims(s, field, &rows, &cols);
+  double* dev = field_plane(s, field);
+  if (!dev) return fail(s, PM_ERR_INVALID_ARGUMENT, "unknown field %d", field);
+  local_row_span(s, rows, true, &ja, &jb);
+  const size_t n = size_t(jb - ja + 1);
+  if (count != n * cols) return fail(s, PM_ERR_INVALID_ARGUMENT, "slab of field %d expects %zu elements, got %zu", field, n * cols, count);
+  CK(cudaSetDevice(s->device));
+  const KP& k = s->kp;
+  if (to_device)
+    CK(cudaMemcpy2DAsync(dev + pm_idx(k, ja, 0), size_t(k.pitch) * 8, host, size_t(cols) * 8, size_t(cols) * 8, n, cudaMemcpyHostToDevice, s->stream));
+  else
+    CK(cudaMemcpy2DAsync(host, size_t(cols) * 8, dev + pm_idx(k, ja, 0), size_t(k.pitch) * 8, size_t(cols) * 8, n, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  if (to_device && field == PM_FIELD_F) s->f_max_valid = false;
+  return PM_OK;
+}
+extern "C" int pm_upload_slab(pm_solver* s, int field, const double* host, size_t count) { return slab_copy(s, field, const_cast<double*>(host), count, true); }
+extern "C" int pm_download_slab(pm_solver* s, int field, double* host, size_t count) { return slab_copy(s, field, host, count, false); }
+
+extern "C" int pm_upload_mask(pm_solver* s, const uint8_t* is_fluid, size_t count) {
+  if (!s || !is_fluid) return PM_ERR_INVALID_ARGUMENT;
+  if (s->cfg.case_id != PM_CASE_STEP) return fail(s, PM_ERR_UNSUPPORTED, "only the step case carries an obstacle mask");
+  if (count != size_t(s->cfg.ny + 2) * (s->cfg.nx + 2)) return fail(s, PM_ERR_INVALID_ARGUMENT, "mask expects (ny+2)*(nx+2) bytes");
+  CK(cudaSetDevice(s->device));
+  return upload_mask_rows(s, is_fluid);
+}
+extern "C" int pm_download_mask(pm_solver* s, uint8_t* is_fluid, size_t count) {
+  if (!s || !is_fluid) return PM_ERR_INVALID_ARGUMENT;
+  const int cols = s->cfg.nx + 2;
+  if (count != size_t(s->cfg.ny + 2) * cols) return fail(s, PM_ERR_INVALID_ARGUMENT, "mask expects (ny+2)*(nx+2) bytes");
+  CK(cudaSetDevice(s->device));
+  int ja, jb;
+  local_row_span(s, s->cfg.ny + 2, false, &ja, &jb);
+  const KP& k = s->kp;
+  CK(cudaMemcpy2DAsync(is_fluid + size_t(k.j0 + ja) * cols, size_t(cols), s->mask + pm_idx(k, ja, 0), size_t(k.pitch),
+                       size_t(cols), size_t(jb - ja + 1), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return PM_OK;
+}
+
+extern "C" int pm_fill_zero(pm_solver* s) {
+  if (!s) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  CK(cudaMemsetAsync(s->base, 0, s->plane * PL_COUNT * sizeof(double), s->stream));
+  s->p_cur = PL_P0;
+  s->f_max_valid = false;
+  return PM_OK;
+}
+extern "C" int pm_fill_random(pm_solver* s, uint64_t seed) {
+  if (!s) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  PMTRY(pm_fill_zero(s));
+  const KP& k = s->kp;
+  for (int field = 0; field < PM_FIELD_COUNT; ++field) {
+    int rows, cols;
+    field_dims(s, field, &rows, &cols);
+    const dim3 b(128, 4), g((cols + 127) / 128, (k.nyl + 2 + 3) / 4);
+    k_fill_random<<<g, b, 0, s->stream>>>(k, field_plane(s, field), field, rows, cols, seed);
+    CKL(s);
+  }
+  s->f_max_valid = false;
+  return PM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// halo exchange between slabs (no-ops on a single rank)
+// ---------------------------------------------------------------------------
+// One halo row each way: my top interior row -> upper rank's row 0; my bottom interior row -> lower rank's row nyl+1.
+static int exchange_halo1(pm_solver* s, double* plane) {
+  if (s->cfg.nranks == 1) return PM_OK;
+  const KP& k = s->kp;
+  std::string e;
+  const size_t n = size_t(k.pitch);
+  double* row_top = plane + size_t(k.padr + k.nyl) * k.pitch;        // send up
+  double* halo_top = plane + size_t(k.padr + k.nyl + 1) * k.pitch;   // recv from up
+  double* row_bot = plane + size_t(k.padr + 1) * k.pitch;            // send down
+  double* halo_bot = plane + size_t(k.padr + 0) * k.pitch;           // recv from down
+  if (!pm_nccl_exchange(&s->nccl, s->stream, k.last_rank ? nullptr : row_top, k.last_rank ? nullptr : halo_top,
+                        k.first_rank ? nullptr : row_bot, k.first_rank ? nullptr : halo_bot, n, &e))
+    return fail(s, PM_ERR_NCCL, "%s", e.c_str());
+  return PM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// phases
+// ---------------------------------------------------------------------------
+extern "C" int pm_apply_bc(pm_solver* s, int which) {
+  if (!s) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  const KP& k = s->kp;
+  double* U = which ? s->pl[PL_US] : s->pl[PL_U];
+  double* V = which ? s->pl[PL_VS] : s->pl[PL_V];
+  const int n = std::max(k.nx, k.nyl) + 2;
+  if (k.case_id == PM_CASE_CAVITY) {
+    if (which) return PM_OK;  // the cavity never applies BCs to (u*,v*)
+    k_bc_cavity<<<(n + 255) / 256, 256, 0, s->stream>>>(k, U, V);
+    CKL(s);
+  } else {
+    k_bc_channel<<<(n + 255) / 256, 256, 0, s->stream>>>(k, U, V);
+    CKL(s);
+    if (k.has_mask) {
+      k_bc_solid<<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->mask, U, V);
+      CKL(s);
+    }
+  }
+  return PM_OK;
+}
+
+extern "C" int pm_predict(pm_solver* s) {
+  if (!s) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  const KP& k = s->kp;
+  PMTRY(exchange_halo1(s, s->pl[PL_U]));
+  PMTRY(exchange_halo1(s, s->pl[PL_V]));
+  if (s->cfg.exact_arith)
+    k_predict<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->mask, s->pl[PL_US], s->pl[PL_VS]);
+  else
+    k_predict<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->mask, s->pl[PL_US], s->pl[PL_VS]);
+  CKL(s);
+  return PM_OK;
+}
+
+extern "C" int pm_source(pm_solver* s) {
+  if (!s) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  const KP& k = s->kp;
+  const bool cav = k.case_id == PM_CASE_CAVITY;
+  const bool exact = s->cfg.exact_arith != 0;
+  PMTRY(exchange_halo1(s, s->pl[PL_VS]));  // f[1][i] reads v*[0][i] of the slab below
+  CK(cudaMemsetAsync(&s->d_state->maxf_bits, 0, 2 * sizeof(unsigned long long), s->stream));
+  double* partial = (!cav && !exact) ? s->d_partial : nullptr;
+  if (exact)
+    k_source<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->mask, s->pl[PL_F], s->d_state, partial);
+  else
+    k_source<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->mask, s->pl[PL_F], s->d_state, partial);
+  CKL(s);
+  if (cav) {
+    // the tolerance rule reads max|f| of this very pass (cavity-01.cpp:628-632)
+    CK(cudaMemcpyAsync(&s->d_state->maxf2_bits, &s->d_state->maxf_bits, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s->stream));
+    s->f_max_valid = true;
+    return PM_OK;
+  }
+  if (s->cfg.nranks > 1) return fail(s, PM_ERR_UNSUPPORTED, "channel/step source mean over slabs is not implemented yet");
+  if (exact) {
+    k_mean_serial<<<1, 32, 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+    CKL(s);
+    k_sub_mean<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+  } else {
+    k_mean_from_partials<<<1, 1024, 0, s->stream>>>(s->d_partial, s->n_partial, k.fluid_count_global, s->d_state);
+    CKL(s);
+    k_sub_mean<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+  }
+  CKL(s);
+  s->f_max_valid = true;
+  return PM_OK;
+}
+
+extern "C" int pm_correct(pm_solver* s) {
+  if (!s) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  const KP& k = s->kp;
+  PMTRY(exchange_halo1(s, s->pl[s->p_cur]));
+  if (s->cfg.exact_arith)
+    k_correct<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->pl[s->p_cur], s->mask, s->pl[PL_U], s->pl[PL_V]);
+  else
+    k_correct<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->pl[s->p_cur], s->mask, s->pl[PL_U], s->pl[PL_V]);
+  CKL(s);
+  return PM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// pressure solve
+// ---------------------------------------------------------------------------
+template <class A, int FORM>
+static int launch_iteration_simple(pm_solver* s, int krel, int kabs) {
+  const KP& k = s->kp;
+  const int method = s->cfg.ppe_method;
+  const bool masked = k.has_mask != 0;
+  const int fuse = masked ? 0 : 1;
+  double* f = s->pl[PL_F];
+  if (method == PM_PPE_JACOBI) {
+    // iterate m lives in plane (m & 1) counted from the plane that held p at solve start
+    const int buf[2] = {s->p_cur, s->p_cur == PL_P0 ? PL_P1 : PL_P0};
+    double* src = s->pl[buf[(kabs - 1) & 1]];
+    double* dst = s->pl[buf[kabs & 1]];
+    k_jacobi<A, FORM><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, src, dst, f, s->mask, s->d_state, s->d_res, krel, fuse);
+    CKL(s);
+    if (masked) {
+      k_pghost_walls<<<(std::max(k.nx, k.nyl) + 255) / 256, 256, 0, s->stream>>>(k, dst, s->d_state, s->d_res, krel);
+      CKL(s);
+      k_pghost_solid<<<cell_grid(k), cell_block(), 0, s->stream>>>(k, dst, s->mask, s->d_state, s->d_res, krel);
+      CKL(s);
+    }
+    PMTRY(exchange_halo1(s, dst));
+    k_residual<A, FORM><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, dst, f, s->mask, s->d_state, s->d_res, krel, 0);
+    CKL(s);
+  } else {
+    double* p = s->pl[s->p_cur];
+    k_rb_colour<A, FORM><<<half_grid(k), cell_block(), 0, s->stream>>>(k, p, f, s->mask, s->d_state, s->d_res, krel, 0, 1, fuse);
+    CKL(s);
+    PMTRY(exchange_halo1(s, p));
+    k_rb_colour<A, FORM><<<half_grid(k), cell_block(), 0, s->stream>>>(k, p, f, s->mask, s->d_state, s->d_res, krel, 1, 0, fuse);
+    CKL(s);
+    if (masked) {
+      k_pghost_walls<<<(std::max(k.nx, k.nyl) + 255) / 256, 256, 0, s->stream>>>(k, p, s->d_state, s->d_res, krel);
+      CKL(s);
+      k_pghost_solid<<<cell_grid(k), cell_block(), 0, s->stream>>>(k, p, s->mask, s->d_state, s->d_res, krel);
+      CKL(s);
+    }
+    PMTRY(exchange_halo1(s, p));
+    k_residual<A, FORM><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, p, f, s->mask, s->d_state, s->d_res, krel, 0);
+    CKL(s);
+  }
+  s->timing.ppe_passes++;
+  return PM_OK;
+}
+
+static int launch_iteration_simple(pm_solver* s, int krel, int kabs) {
+  const bool cav = s->kp.case_id == PM_CASE_CAVITY;
+  if (s->cfg.exact_arith) return cav ? launch_iteration_simple<Exact, 0>(s, krel, kabs) : launch_iteration_simple<Exact, 1>(s, krel, kabs);
+  return cav ? launch_iteration_simple<Fast, 0>(s, krel, kabs) : launch_iteration_simple<Fast, 1>(s, krel, kabs);
+}
+
+static int tiled_solve(pm_solver* s, int* iters, double* res) {
+  (void)iters; (void)res;
+  return fail(s, PM_ERR_UNSUPPORTED, "tiled path not built");
+}
+
+static int read_state(pm_solver* s) {
+  CK(cudaMemcpyAsync(s->h_state, s->d_state, sizeof(PpeState), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return PM_OK;
+}
+
+extern "C" int pm_ppe_solve(pm_solver* s, pm_ppe_result* out) {
+  if (!s) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  const KP& k = s->kp;
+  const pm_config& c = s->cfg;
+  const bool cav = k.case_id == PM_CASE_CAVITY;
+  if (c.ppe_method == PM_PPE_SOR_LEX) return fail(s, PM_ERR_UNSUPPORTED, "sor-lex (wavefront) kernel is not built yet");
+  if (c.nranks > 1 && s->nccl.comm == nullptr) return fail(s, PM_ERR_NCCL, "communicator missing");
+
+  CK(cudaEventRecord(s->ev_a, s->stream));
+  if (!s->f_max_valid) {
+    CK(cudaMemsetAsync(&s->d_state->maxf2_bits, 0, sizeof(unsigned long long), s->stream));
+    k_max_f<<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+    CKL(s);
+    s->f_max_valid = true;
+  }
+  if (c.nranks > 1) {
+    std::string e;
+    if (!pm_nccl_allreduce_max_u64(&s->nccl, s->stream, &s->d_state->maxf2_bits, 1, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
+  }
+  if (cav) {  // cold start from p == 0, both buffers (cavity-01.cpp:610-611)
+    CK(cudaMemsetAsync(s->pl[PL_P0], 0, s->plane * sizeof(double), s->stream));
+    CK(cudaMemsetAsync(s->pl[PL_P1], 0, s->plane * sizeof(double), s->stream));
+    s->p_cur = PL_P0;
+  }
+  if (!cav && c.ppe_method == PM_PPE_JACOBI) {
+    k_copy_corners<<<1, 32, 0, s->stream>>>(k, s->pl[s->p_cur], s->pl[s->p_cur == PL_P0 ? PL_P1 : PL_P0]);
+    CKL(s);
+  }
+  CK(cudaMemsetAsync(s->d_res, 0, size_t(c.max_iters + 2) * sizeof(unsigned long long), s->stream));
+  k_ppe_begin<<<1, 1, 0, s->stream>>>(k, s->d_state);
+  CKL(s);
+
+  int iters = 0;
+  double res = 0.0;
+  if (s->use_tiled) {
+    PMTRY(tiled_solve(s, &iters, &res));
+  } else {
+    if (c.ppe_method != PM_PPE_JACOBI) PMTRY(exchange_halo1(s, s->pl[s->p_cur]));
+    const int K = c.max_iters;
+    int kdone = 0;
+    int chunk = c.poll_chunk > 0 ? c.poll_chunk : std::max(4, std::min(256, s->last_iters / 8));
+    bool done = false;
+    while (kdone < K && !done) {
+      const int n = std::min(chunk, K - kdone);
+      for (int q = 1; q <= n; ++q) PMTRY(launch_iteration_simple(s, kdone + q, kdone + q));
+      kdone += n;
+      PMTRY(read_state(s));
+      done = s->h_state->done != 0;
+      if (c.poll_chunk <= 0) chunk = std::min(256, chunk * 2);
+    }
+    if (!done) {
+      // the cap ended the loop; one more look at the flag logic is not needed: iterate K is final
+      PMTRY(read_state(s));
+    }
+    iters = s->h_state->done ? s->h_state->iters : K;
+    if (K == 0) iters = 0;
+    unsigned long long bits = 0;
+    if (iters >= 1) {
+      CK(cudaMemcpyAsync(s->h_res, s->d_res + iters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+      CK(cudaStreamSynchronize(s->stream));
+      bits = s->h_res[0];
+      std::memcpy(&res, &bits, 8);
+    } else {
+      res = s->h_state->res_init;
+    }
+    if (c.ppe_method == PM_PPE_JACOBI && (iters & 1)) s->p_cur = (s->p_cur == PL_P0) ? PL_P1 : PL_P0;
+  }
+  CK(cudaEventRecord(s->ev_b, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, s->ev_a, s->ev_b));
+  s->timing.ppe_ms += ms;
+  s->last_iters = iters;
+  if (out) {
+    out->iterations = iters;
+    out->hit_cap = iters >= c.max_iters;
+    out->residual = res;
+    out->tolerance = s->h_state->tol;
+    unsigned long long mb = s->h_state->maxf2_bits;
+    std::memcpy(&out->max_source, &mb, 8);
+  }
+  return PM_OK;
+}
+
+extern "C" int pm_step(pm_solver* s, int nsteps, pm_ppe_result* last) {
+  if (!s || nsteps < 0) return PM_ERR_INVALID_ARGUMENT;
+  pm_ppe_result r{};
+  for (int n = 0; n < nsteps; ++n) {
+    if (s->kp.case_id == PM_CASE_CAVITY) {  // cavity-01.cpp:387-390
+      PMTRY(pm_apply_bc(s, 0));
+      PMTRY(pm_predict(s));
+      PMTRY(pm_source(s));
+      PMTRY(pm_ppe_solve(s, &r));
+      PMTRY(pm_correct(s));
+    } else {  // channel-01.cpp:368-375
+      PMTRY(pm_predict(s));
+      PMTRY(pm_apply_bc(s, 1));
+      PMTRY(pm_source(s));
+      PMTRY(pm_ppe_solve(s, &r));
+      PMTRY(pm_correct(s));
+      PMTRY(pm_apply_bc(s, 0));
+    }
+  }
+  if (last) *last = r;
+  return PM_OK;
+}
+
+extern "C" int pm_diagnostics(pm_solver* s, double* max_div, double* avg_ke) {
+  if (!s || !max_div || !avg_ke) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  const KP& k = s->kp;
+  CK(cudaMemsetAsync(&s->d_state->div_bits, 0, sizeof(unsigned long long), s->stream));
+  PMTRY(exchange_halo1(s, s->pl[PL_V]));
+  k_diag<<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->mask, s->d_state, s->d_partial);
+  CKL(s);
+  k_sum_partials<<<1, 1024, 0, s->stream>>>(s->d_partial, s->n_partial, s->d_state);
+  CKL(s);
+  if (s->cfg.nranks > 1) {
+    std::string e;
+    if (!pm_nccl_allreduce_max_u64(&s->nccl, s->stream, &s->d_state->div_bits, 1, &e) ||
+        !pm_nccl_allreduce_sum_f64(&s->nccl, s->stream, &s->d_state->ke_sum, 1, &e))
+      return fail(s, PM_ERR_NCCL, "%s", e.c_str());
+  }
+  PMTRY(read_state(s));
+  unsigned long long b = s->h_state->div_bits;
+  std::memcpy(max_div, &b, 8);
+  const double ke = s->h_state->ke_sum;
+  if (k.case_id == PM_CASE_STEP) *avg_ke = k.fluid_count_global > 0 ? ke / k.fluid_count_global : 0.0;
+  else *avg_ke = ke / (k.nx * k.ny);
+  return PM_OK;
+}
+
+extern "C" int pm_get_timing(pm_solver* s, pm_timing* t) {
+  if (!s || !t) return PM_ERR_INVALID_ARGUMENT;
+  *t = s->timing;
+  return PM_OK;
+}
+
+extern "C" int pm_timer_start(pm_solver* s) {
+  if (!s) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  CK(cudaEventRecord(s->ev_t0, s->stream));
+  return PM_OK;
+}
+extern "C" int pm_timer_stop(pm_solver* s, double* elapsed_ms) {
+  if (!s || !elapsed_ms) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  CK(cudaEventRecord(s->ev_t1, s->stream));
+  CK(cudaEventSynchronize(s->ev_t1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1));
+  *elapsed_ms = ms;
+  return PM_OK;
+}

@@ -1,0 +1,491 @@
+// pm_kernels_simple.cuh — one kernel per reference loop, global-memory
+// stencils with coalesced row access.  This is the general path: every case, the obstacle mask,
+// any grid size, slabs.  The bandwidth path for large unmasked grids is pm_kernels_tiled.cuh.
+#pragma once
+#include "pm_common.cuh"
+
+#define PM_BX 128
+#define PM_BY 4
+
+// ---------------------------------------------------------------------------
+// k1  velocity BC ghost fill
+// ---------------------------------------------------------------------------
+// cavity-01.cpp:523-543.  One thread per ghost cell; reads only interior faces.
+__global__ void k_bc_cavity(const __grid_constant__ KP k, double* __restrict__ U, double* __restrict__ V) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t <= k.nx) {
+    if (k.last_rank) U[pm_idx(k, k.nyl + 1, t)] = k.two_uref - U[pm_idx(k, k.nyl, t)];
+    if (k.first_rank) U[pm_idx(k, 0, t)] = -U[pm_idx(k, 1, t)];
+  }
+  if (t <= k.nyl) {  // v rows jl = 0..nyl (row 0 is a halo row on rank > 0; its ghosts follow the same rule)
+    V[pm_idx(k, t, k.nx + 1)] = -V[pm_idx(k, t, k.nx)];
+    V[pm_idx(k, t, 0)] = -V[pm_idx(k, t, 1)];
+  }
+}
+
+// channel-01.cpp:513-529 and backwards_step-01.cpp:616-652 (walls; solid faces are k_bc_solid).
+// The reference applies inlet/outlet columns first, then the wall rows for i = 0..nx, which read
+// the just-set column values at the corners.  Here a row thread derives the
+// corner value it would have read, so no thread depends on another.
+__global__ void k_bc_channel(const __grid_constant__ KP k, double* __restrict__ U, double* __restrict__ V) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nx = k.nx, nyl = k.nyl;
+  // column phase: local rows
+  if (t <= nyl + 1) {
+    const int jl = t, j = k.j0 + jl;
+    if (j >= 1 && j <= k.ny && jl >= 0) {  // u rows 1..ny (local rows 0..nyl+1 may be halo rows of a neighbour: same rule)
+      const double uin = (k.case_id == PM_CASE_STEP && j > k.inlet_j_max) ? 0.0 : k.uref;
+      U[pm_idx(k, jl, 0)] = uin;
+      U[pm_idx(k, jl, nx)] = U[pm_idx(k, jl, nx - 1)];
+    }
+    if (j >= 0 && j <= k.ny && jl <= nyl) {  // v rows 0..ny
+      V[pm_idx(k, jl, 0)] = 0.0;
+      const double vo = V[pm_idx(k, jl, nx)];  // read BEFORE the wall rows zero v[0][nx] / v[ny][nx]
+      V[pm_idx(k, jl, nx + 1)] = vo;
+      if (j == 0 || j == k.ny) V[pm_idx(k, jl, nx)] = 0.0;  // the wall-row write for i = nx, issued by this thread to keep the order
+    }
+  }
+  // row phase
+  if (t <= nx) {
+    const int i = t;
+    if (k.first_rank) {
+      if (i >= 1 && i < nx) V[pm_idx(k, 0, i)] = 0.0;
+      double s;  // value of U[1][i] after the column phase
+      if (i == 0) s = (k.case_id == PM_CASE_STEP && 1 > k.inlet_j_max) ? 0.0 : k.uref;
+      else if (i == nx) s = U[pm_idx(k, 1, nx - 1)];
+      else s = U[pm_idx(k, 1, i)];
+      U[pm_idx(k, 0, i)] = -s;
+    }
+    if (k.last_rank) {
+      if (i >= 1 && i < nx) V[pm_idx(k, nyl, i)] = 0.0;
+      double s;
+      if (i == 0) s = (k.case_id == PM_CASE_STEP && k.ny > k.inlet_j_max) ? 0.0 : k.uref;
+      else if (i == nx) s = U[pm_idx(k, nyl, nx - 1)];
+      else s = U[pm_idx(k, nyl, i)];
+      U[pm_idx(k, nyl + 1, i)] = -s;
+    }
+  }
+}
+
+// backwards_step-01.cpp:654-682: zero the faces between a solid cell and a fluid neighbour.
+// Runs after k_bc_channel (the wall ghosts read the pre-zero values, as in the reference).
+__global__ void k_bc_solid(const __grid_constant__ KP k, const uint8_t* __restrict__ M, double* __restrict__ U,
+                           double* __restrict__ V) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > k.nx || jl > k.nyl) return;
+  const int j = k.j0 + jl;
+  if (M[pm_idx(k, jl, i)]) return;
+  if (i < k.nx && M[pm_idx(k, jl, i + 1)]) U[pm_idx(k, jl, i)] = 0.0;
+  if (i > 1 && M[pm_idx(k, jl, i - 1)]) U[pm_idx(k, jl, i - 1)] = 0.0;
+  if (j < k.ny && M[pm_idx(k, jl + 1, i)]) V[pm_idx(k, jl, i)] = 0.0;
+  if (j > 1 && M[pm_idx(k, jl - 1, i)]) V[pm_idx(k, jl - 1, i)] = 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// k2+k3  predictor: u* and v* in one pass (cavity-01.cpp:553-602; channel-01.cpp:553-602;
+//        backwards_step-01.cpp:752-819)
+// ---------------------------------------------------------------------------
+template <class A>
+__global__ void __launch_bounds__(PM_BX* PM_BY)
+    k_predict(const __grid_constant__ KP k, const double* __restrict__ u, const double* __restrict__ v,
+              const uint8_t* __restrict__ M, double* __restrict__ us, double* __restrict__ vs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > k.nx || jl > k.nyl) return;
+  const int j = k.j0 + jl;
+  const size_t c = pm_idx(k, jl, i);
+  const int P = k.pitch;
+  const double uc = u[c], uw = u[c - 1], vc = v[c], vS = v[c - P];
+  const bool do_u = i <= k.nx - 1, do_v = j <= k.ny - 1;
+  const double ue_ = do_u ? u[c + 1] : 0.0;  // u has nx+1 columns: i+1 exists only for i <= nx-1
+  const double uN = u[c + P], uS = u[c - P];
+  const double ve_ = v[c + 1], vw_ = v[c - 1];
+  bool fl_c = true, fl_e = true, fl_n = true;
+  if (k.has_mask) { fl_c = M[c]; fl_e = M[c + 1]; fl_n = M[c + P]; }
+  if (do_u) {
+    double r = 0.0;
+    if (fl_c || fl_e) {
+      const double t2 = A::mul(2.0, uc);
+      const double diff = A::mul(k.nu, A::add(A::mul(A::add(A::sub(ue_, t2), uw), k.idx2),
+                                              A::mul(A::add(A::sub(uN, t2), uS), k.idy2)));
+      const double ue = A::mul(0.5, A::add(uc, ue_));
+      const double uwf = A::mul(0.5, A::add(uw, uc));
+      const double cx = A::mul(A::sub(A::mul(ue, ue), A::mul(uwf, uwf)), k.idx);
+      const double vn = A::mul(0.5, A::add(vc, ve_));
+      const double vsf = A::mul(0.5, A::add(vS, v[c - P + 1]));
+      const double un = A::mul(0.5, A::add(uN, uc));
+      const double usf = A::mul(0.5, A::add(uS, uc));
+      const double cy = A::mul(A::sub(A::mul(vn, un), A::mul(vsf, usf)), k.idy);
+      r = A::add(uc, A::mul(k.dt, A::sub(A::sub(diff, cx), cy)));
+    }
+    us[c] = r;
+  }
+  if (do_v) {
+    double r = 0.0;
+    if (fl_c || fl_n) {
+      const double vN = v[c + P];
+      const double t2 = A::mul(2.0, vc);
+      const double diff = A::mul(k.nu, A::add(A::mul(A::add(A::sub(ve_, t2), vw_), k.idx2),
+                                              A::mul(A::add(A::sub(vN, t2), vS), k.idy2)));
+      const double vn = A::mul(0.5, A::add(vc, vN));
+      const double vsf = A::mul(0.5, A::add(vS, vc));
+      const double cy = A::mul(A::sub(A::mul(vn, vn), A::mul(vsf, vsf)), k.idy);
+      const double ue = A::mul(0.5, A::add(uc, uN));
+      const double uwf = A::mul(0.5, A::add(uw, u[c + P - 1]));
+      const double ve = A::mul(0.5, A::add(vc, ve_));
+      const double vw = A::mul(0.5, A::add(vw_, vc));
+      const double cx = A::mul(A::sub(A::mul(ue, ve), A::mul(uwf, vw)), k.idx);
+      r = A::add(vc, A::mul(k.dt, A::sub(A::sub(diff, cy), cx)));
+    }
+    vs[c] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k4  divergence source + max|f|  (cavity-01.cpp:622-630; channel-01.cpp:613-619;
+//     backwards_step-01.cpp:830-841).  Also per-block partial sums for the mean.
+// ---------------------------------------------------------------------------
+template <class A>
+__global__ void __launch_bounds__(PM_BX* PM_BY)
+    k_source(const __grid_constant__ KP k, const double* __restrict__ us, const double* __restrict__ vs,
+             const uint8_t* __restrict__ M, double* __restrict__ f, PpeState* __restrict__ st,
+             double* __restrict__ partial /* one per block, or null */) {
+  __shared__ double sh[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  double a = 0.0, val = 0.0;
+  if (i <= k.nx && jl <= k.nyl) {
+    const size_t c = pm_idx(k, jl, i);
+    if (!k.has_mask || M[c]) {
+      const double du = A::mul(A::sub(us[c], us[c - 1]), k.idx);
+      const double dv = A::mul(A::sub(vs[c], vs[c - k.pitch]), k.idy);
+      val = A::mul(k.src_coef, A::add(du, dv));
+      a = fabs(val);
+    }
+    f[c] = val;
+  }
+  const double m = block_max(a, sh);
+  if (threadIdx.x == 0 && threadIdx.y == 0) atomic_max_nonneg(&st->maxf_bits, m);
+  if (partial) {
+    const double s = block_sum(val, sh);
+    if (threadIdx.x == 0 && threadIdx.y == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+// k5 (fast policy): fixed-shape tree over the per-block partial sums, one block.
+__global__ void k_mean_from_partials(const double* __restrict__ partial, int n, int count, PpeState* __restrict__ st) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) s += partial[t];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) st->mean = count > 0 ? s / double(count) : 0.0;
+}
+// k5 (exact policy): the reference's serial row-major sum (channel-01.cpp:622-625), one warp,
+// every lane adding the same 32 shuffled values in index order.
+__global__ void k_mean_serial(const __grid_constant__ KP k, const double* __restrict__ f, const uint8_t* __restrict__ M,
+                              PpeState* __restrict__ st) {
+  const int lane = threadIdx.x;
+  double s = 0.0;
+  int cnt = 0;
+  for (int jl = 1; jl <= k.nyl; ++jl)
+    for (int ib = 1; ib <= k.nx; ib += 32) {
+      const int i = ib + lane;
+      double x = 0.0;
+      int use = 0;
+      if (i <= k.nx) {
+        const size_t c = pm_idx(k, jl, i);
+        use = !k.has_mask || M[c];
+        x = f[c];
+      }
+      const int n = min(32, k.nx - ib + 1);
+      for (int q = 0; q < n; ++q) {
+        const double xq = __shfl_sync(0xffffffffu, x, q);
+        const int uq = __shfl_sync(0xffffffffu, use, q);
+        if (uq) { s = __dadd_rn(s, xq); ++cnt; }
+      }
+    }
+  if (lane == 0) st->mean = cnt > 0 ? __ddiv_rn(s, double(cnt)) : 0.0;
+}
+// k5/k6: f -= mean on (fluid) cells when max|f| > 0, and max|f| of the result
+// (channel-01.cpp:621-628, :643-646).
+template <class A>
+__global__ void __launch_bounds__(PM_BX* PM_BY)
+    k_sub_mean(const __grid_constant__ KP k, double* __restrict__ f, const uint8_t* __restrict__ M,
+               PpeState* __restrict__ st) {
+  __shared__ double sh[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const bool apply = st->maxf_bits != 0ull;
+  const double mean = st->mean;
+  double a = 0.0;
+  if (i <= k.nx && jl <= k.nyl) {
+    const size_t c = pm_idx(k, jl, i);
+    if (!k.has_mask || M[c]) {
+      double x = f[c];
+      if (apply) { x = A::sub(x, mean); f[c] = x; }
+      a = fabs(x);
+    }
+  }
+  const double m = block_max(a, sh);
+  if (threadIdx.x == 0 && threadIdx.y == 0) atomic_max_nonneg(&st->maxf2_bits, m);
+}
+// max|f| only (cavity, or when pm_ppe_solve is called on an uploaded f).
+__global__ void __launch_bounds__(PM_BX* PM_BY)
+    k_max_f(const __grid_constant__ KP k, const double* __restrict__ f, const uint8_t* __restrict__ M,
+            PpeState* __restrict__ st) {
+  __shared__ double sh[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  double a = 0.0;
+  if (i <= k.nx && jl <= k.nyl) {
+    const size_t c = pm_idx(k, jl, i);
+    if (!k.has_mask || M[c]) a = fabs(f[c]);
+  }
+  const double m = block_max(a, sh);
+  if (threadIdx.x == 0 && threadIdx.y == 0) atomic_max_nonneg(&st->maxf2_bits, m);
+}
+
+// k6: tolerance and loop entry (cavity-01.cpp:618,632; channel-01.cpp:647-649). One thread.
+__global__ void k_ppe_begin(const __grid_constant__ KP k, PpeState* __restrict__ st) {
+  const double mx = __longlong_as_double((long long)st->maxf2_bits);
+  double tol, r0;
+  if (k.case_id == PM_CASE_CAVITY) {
+    tol = __dmul_rn(k.tol_factor, mx);
+    r0 = 1.0;
+  } else {
+    tol = fmax(__dmul_rn(k.tol_factor, (mx > 0 ? mx : 1.0)), k.abs_tol);
+    r0 = __dadd_rn(tol, 1.0);
+  }
+  st->tol = tol;
+  st->res_init = r0;
+  st->iters = 0;
+  st->done = !(r0 > tol) || !(0 < k.max_iters);
+  st->kbase = 0;
+}
+
+// ---------------------------------------------------------------------------
+// k7  one colour of a red-black SOR sweep, in place.  colour = (i + j) & 1 with GLOBAL j.
+//     The thread that updates a wall-adjacent cell also refreshes the ghost behind it
+//     (channel-01.cpp:531-541): that ghost is read by no other thread.
+// ---------------------------------------------------------------------------
+template <class A, int FORM /*0 cavity, 1 channel*/>
+__global__ void __launch_bounds__(PM_BX* PM_BY)
+    k_rb_colour(const __grid_constant__ KP k, double* __restrict__ p, const double* __restrict__ f,
+                const uint8_t* __restrict__ M, PpeState* __restrict__ st, const unsigned long long* __restrict__ res_bits,
+                int kiter_rel, int colour, int first_of_iter, int fuse_ghosts) {
+  const int kiter = st->kbase + kiter_rel;
+  if (ppe_stop_before(st, res_bits, kiter, k.max_iters)) {
+    if (first_of_iter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0 && !st->done &&
+        kiter <= k.max_iters) {
+      st->iters = kiter - 1;
+      st->done = 1;
+    }
+    return;
+  }
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (jl > k.nyl) return;
+  const int j = k.j0 + jl;
+  const int i = 1 + ((colour + j + 1) & 1) + 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (i > k.nx) return;
+  const size_t c = pm_idx(k, jl, i);
+  if (k.has_mask && !M[c]) return;
+  const int P = k.pitch;
+  const double pc = p[c], pe = p[c + 1], pw = p[c - 1], pn = p[c + P], ps = p[c - P], fc = f[c];
+  double r;
+  if (FORM == 0) r = upd_cavity<A>(k, j, i, pc, pe, pw, pn, ps, fc);
+  else r = upd_channel<A>(k, pc, pe, pw, pn, ps, fc);
+  p[c] = r;
+  if (FORM == 1 && fuse_ghosts) {
+    if (i == 1) p[c - 1] = r;
+    if (i == k.nx) p[c + 1] = 0.0;
+    if (j == 1) p[c - P] = r;
+    if (j == k.ny) p[c + P] = r;
+  }
+}
+
+// Jacobi sweep src -> dst (every neighbour from the previous iterate).
+template <class A, int FORM>
+__global__ void __launch_bounds__(PM_BX* PM_BY)
+    k_jacobi(const __grid_constant__ KP k, const double* __restrict__ src, double* __restrict__ dst,
+             const double* __restrict__ f, const uint8_t* __restrict__ M, PpeState* __restrict__ st,
+             const unsigned long long* __restrict__ res_bits, int kiter_rel, int fuse_ghosts) {
+  const int kiter = st->kbase + kiter_rel;
+  if (ppe_stop_before(st, res_bits, kiter, k.max_iters)) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0 && !st->done && kiter <= k.max_iters) {
+      st->iters = kiter - 1;
+      st->done = 1;
+    }
+    return;
+  }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > k.nx || jl > k.nyl) return;
+  const int j = k.j0 + jl;
+  const size_t c = pm_idx(k, jl, i);
+  const int P = k.pitch;
+  const double pc = src[c];
+  double r = pc;
+  if (!k.has_mask || M[c]) {
+    const double pe = src[c + 1], pw = src[c - 1], pn = src[c + P], ps = src[c - P], fc = f[c];
+    if (FORM == 0) r = upd_cavity<A>(k, j, i, pc, pe, pw, pn, ps, fc);
+    else r = upd_channel<A>(k, pc, pe, pw, pn, ps, fc);
+  }
+  dst[c] = r;
+  if (FORM == 1 && fuse_ghosts) {
+    if (i == 1) dst[c - 1] = r;
+    if (i == k.nx) dst[c + 1] = 0.0;
+    if (j == 1) dst[c - P] = r;
+    if (j == k.ny) dst[c + P] = r;
+  }
+}
+
+// k8 (mask case): wall ghosts as their own pass, then solid-cell extrapolation
+// (backwards_step-01.cpp:685-740).  The wall ghosts read the pre-extrapolation values.
+__global__ void k_pghost_walls(const __grid_constant__ KP k, double* __restrict__ p, PpeState* __restrict__ st,
+                               const unsigned long long* __restrict__ res_bits, int kiter_rel) {
+  if (ppe_stop_before(st, res_bits, st->kbase + kiter_rel, k.max_iters)) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (t <= k.nyl) {
+    p[pm_idx(k, t, 0)] = p[pm_idx(k, t, 1)];
+    p[pm_idx(k, t, k.nx + 1)] = 0.0;
+  }
+  if (t <= k.nx) {
+    if (k.first_rank) p[pm_idx(k, 0, t)] = p[pm_idx(k, 1, t)];
+    if (k.last_rank) p[pm_idx(k, k.nyl + 1, t)] = p[pm_idx(k, k.nyl, t)];
+  }
+}
+__global__ void __launch_bounds__(PM_BX* PM_BY)
+    k_pghost_solid(const __grid_constant__ KP k, double* __restrict__ p, const uint8_t* __restrict__ M,
+                   PpeState* __restrict__ st, const unsigned long long* __restrict__ res_bits, int kiter_rel) {
+  if (ppe_stop_before(st, res_bits, st->kbase + kiter_rel, k.max_iters)) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > k.nx || jl > k.nyl) return;
+  const int j = k.j0 + jl;
+  const size_t c = pm_idx(k, jl, i);
+  if (M[c]) return;
+  const int P = k.pitch;
+  double s = 0.0;
+  int n = 0;
+  if (i > 1 && M[c - 1]) { s = __dadd_rn(s, p[c - 1]); ++n; }
+  if (i < k.nx && M[c + 1]) { s = __dadd_rn(s, p[c + 1]); ++n; }
+  if (j > 1 && M[c - P]) { s = __dadd_rn(s, p[c - P]); ++n; }
+  if (j < k.ny && M[c + P]) { s = __dadd_rn(s, p[c + P]); ++n; }
+  if (n > 0) p[c] = __ddiv_rn(s, double(n));
+}
+
+// k9  residual max-norm of the current iterate -> res_bits[kiter]
+//     (cavity-01.cpp:659-677; channel-01.cpp:673-681; backwards_step-01.cpp:917-930)
+template <class A, int FORM>
+__global__ void __launch_bounds__(PM_BX* PM_BY)
+    k_residual(const __grid_constant__ KP k, const double* __restrict__ p, const double* __restrict__ f,
+               const uint8_t* __restrict__ M, PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits,
+               int kiter_rel, int force) {
+  __shared__ double sh[32];
+  const int kiter = st->kbase + kiter_rel;
+  if (!force && ppe_stop_before(st, res_bits, kiter, k.max_iters)) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  double a = 0.0;
+  if (i <= k.nx && jl <= k.nyl) {
+    const size_t c = pm_idx(k, jl, i);
+    if (!k.has_mask || M[c]) {
+      const int P = k.pitch;
+      const double pc = p[c], pe = p[c + 1], pw = p[c - 1], pn = p[c + P], ps = p[c - P], fc = f[c];
+      double r;
+      if (FORM == 0) r = res_cavity<A>(k, k.j0 + jl, i, pc, pe, pw, pn, ps, fc, k.idx2);
+      else r = res_channel<A>(k, pc, pe, pw, pn, ps, fc);
+      a = fabs(r);
+    }
+  }
+  const double m = block_max(a, sh);
+  if (threadIdx.x == 0 && threadIdx.y == 0) atomic_max_nonneg(&res_bits[kiter], m);
+}
+
+// ---------------------------------------------------------------------------
+// k10  velocity correction (cavity-01.cpp:695-711; channel-01.cpp:693-702;
+//      backwards_step-01.cpp:944-976)
+// ---------------------------------------------------------------------------
+template <class A>
+__global__ void __launch_bounds__(PM_BX* PM_BY)
+    k_correct(const __grid_constant__ KP k, const double* __restrict__ us, const double* __restrict__ vs,
+              const double* __restrict__ p, const uint8_t* __restrict__ M, double* __restrict__ u,
+              double* __restrict__ v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > k.nx || jl > k.nyl) return;
+  const int j = k.j0 + jl;
+  const size_t c = pm_idx(k, jl, i);
+  const double pc = p[c];
+  bool fl_c = true, fl_e = true, fl_n = true;
+  if (k.has_mask) { fl_c = M[c]; fl_e = M[c + 1]; fl_n = M[c + k.pitch]; }
+  if (i <= k.nx - 1) {
+    const bool valid = (i == k.nx - 1) || fl_c || fl_e;
+    u[c] = valid ? A::sub(us[c], A::mul(k.cu, A::sub(p[c + 1], pc))) : 0.0;
+  }
+  if (j <= k.ny - 1) {
+    const bool valid = (j == k.ny - 1) || fl_c || fl_n;
+    v[c] = valid ? A::sub(vs[c], A::mul(k.cv, A::sub(p[c + k.pitch], pc))) : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k11  diagnostics (cavity-01.cpp:741-766; channel-01.cpp:733-759)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(PM_BX* PM_BY)
+    k_diag(const __grid_constant__ KP k, const double* __restrict__ u, const double* __restrict__ v,
+           const uint8_t* __restrict__ M, PpeState* __restrict__ st, double* __restrict__ partial) {
+  __shared__ double sh[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  double ke = 0.0, d = 0.0;
+  if (i <= k.nx && jl <= k.nyl) {
+    const size_t c = pm_idx(k, jl, i);
+    if (!k.has_mask || M[c]) {
+      const double uc = __dmul_rn(0.5, __dadd_rn(u[c - 1], u[c]));
+      const double vc = __dmul_rn(0.5, __dadd_rn(v[c - k.pitch], v[c]));
+      ke = __dmul_rn(0.5, __dadd_rn(__dmul_rn(uc, uc), __dmul_rn(vc, vc)));
+      if (k.case_id == PM_CASE_CAVITY)
+        d = __dmul_rn(__dsub_rn(__dadd_rn(__dsub_rn(u[c], u[c - 1]), v[c]), v[c - k.pitch]), k.idx);
+      else
+        d = __dadd_rn(__dmul_rn(__dsub_rn(u[c], u[c - 1]), k.idx), __dmul_rn(__dsub_rn(v[c], v[c - k.pitch]), k.idy));
+      d = fabs(d);
+    }
+  }
+  const double m = block_max(d, sh);
+  if (threadIdx.x == 0 && threadIdx.y == 0) atomic_max_nonneg(&st->div_bits, m);
+  const double s = block_sum(ke, sh);
+  if (threadIdx.x == 0 && threadIdx.y == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+__global__ void k_sum_partials(const double* __restrict__ partial, int n, PpeState* __restrict__ st) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) s += partial[t];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) st->ke_sum = s;
+}
+
+// The four corner ghosts of p are never written by any sweep; a ping-pong (Jacobi) solve carries
+// them into the second buffer so both hold the same field outside the stencil's reach.
+__global__ void k_copy_corners(const __grid_constant__ KP k, const double* __restrict__ src, double* __restrict__ dst) {
+  const int t = threadIdx.x;
+  if (t >= 4) return;
+  const int jl = (t & 2) ? k.nyl + 1 : 0, i = (t & 1) ? k.nx + 1 : 0;
+  if ((jl == 0 && !k.first_rank) || (jl != 0 && !k.last_rank)) return;
+  dst[pm_idx(k, jl, i)] = src[pm_idx(k, jl, i)];
+}
+
+// ---------------------------------------------------------------------------
+// synthetic state and layout conversion
+// ---------------------------------------------------------------------------
+// value(field, j, i) keyed by the reference flat index j*cols + i with GLOBAL j.
+__global__ void k_fill_random(const __grid_constant__ KP k, double* __restrict__ a, int field, int rows_global,
+                              int cols, uint64_t seed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y;  // local rows 0..nyl+1
+  if (i >= cols || jl > k.nyl + 1) return;
+  const int j = k.j0 + jl;
+  if (j >= rows_global) return;
+  a[pm_idx(k, jl, i)] = pm_synth(seed, field, uint64_t(j) * uint64_t(cols) + uint64_t(i));
+}

@@ -60,9 +60,9 @@ def field_shape(field, nx, ny):
 
 EXPORTS = [
     "pm_config_init", "pm_slab_range", "pm_create", "pm_destroy", "pm_last_error", "pm_status_string",
-    "pm_abi_version", "pm_nccl_unique_id", "pm_upload", "pm_download", "pm_upload_mask", "pm_download_mask",
+    "pm_abi_version", "pm_nccl_unique_id", "pm_upload", "pm_download", "pm_slab_rows", "pm_upload_slab", "pm_download_slab", "pm_upload_mask", "pm_download_mask",
     "pm_fill_random", "pm_fill_zero", "pm_apply_bc", "pm_predict", "pm_source", "pm_ppe_solve", "pm_correct",
-    "pm_step", "pm_diagnostics", "pm_sync", "pm_get_timing",
+    "pm_step", "pm_diagnostics", "pm_sync", "pm_get_timing", "pm_timer_start", "pm_timer_stop",
 ]
 
 _lib = None
@@ -88,6 +88,9 @@ def lib():
     L.pm_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     L.pm_upload.argtypes = [vp, C.c_int, dp, C.c_size_t]
     L.pm_download.argtypes = [vp, C.c_int, dp, C.c_size_t]
+    L.pm_slab_rows.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.pm_upload_slab.argtypes = [vp, C.c_int, dp, C.c_size_t]
+    L.pm_download_slab.argtypes = [vp, C.c_int, dp, C.c_size_t]
     L.pm_upload_mask.argtypes = [vp, C.POINTER(C.c_uint8), C.c_size_t]
     L.pm_download_mask.argtypes = [vp, C.POINTER(C.c_uint8), C.c_size_t]
     L.pm_fill_random.argtypes = [vp, C.c_uint64]
@@ -99,6 +102,8 @@ def lib():
     L.pm_step.argtypes = [vp, C.c_int, C.POINTER(PmPpeResult)]
     L.pm_diagnostics.argtypes = [vp, dp, dp]
     L.pm_get_timing.argtypes = [vp, C.POINTER(PmTiming)]
+    L.pm_timer_start.argtypes = [vp]
+    L.pm_timer_stop.argtypes = [vp, dp]
     _lib = L
     return L
 
@@ -197,6 +202,26 @@ class Solver:
 
     def sync(self):
         self._ck(lib().pm_sync(self._h))
+
+    def slab_rows(self, field):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self._ck(lib().pm_slab_rows(self._h, field, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def upload_slab_ptr(self, field, ptr, count):
+        """This rank's rows from a raw host pointer (e.g. a pinned torch tensor's data_ptr())."""
+        self._ck(lib().pm_upload_slab(self._h, field, C.cast(ptr, C.POINTER(C.c_double)), count))
+
+    def download_slab_ptr(self, field, ptr, count):
+        self._ck(lib().pm_download_slab(self._h, field, C.cast(ptr, C.POINTER(C.c_double)), count))
+
+    def timer_start(self):
+        self._ck(lib().pm_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(lib().pm_timer_stop(self._h, C.byref(ms)))
+        return ms.value
 
     def timing(self):
         t = PmTiming()

@@ -141,6 +141,11 @@ int pm_nccl_unique_id(uint8_t out[128]);
  * each rank copies only its own slab (plus halo rows) from/to the global array. */
 int pm_upload(pm_solver* s, int field, const double* host, size_t count);
 int pm_download(pm_solver* s, int field, double* host, size_t count);
+/* Slab-local variants: `host` holds only this rank's rows, global rows j0 .. j0+ny_local+1 (clipped to
+ * the field's row count), i.e. local rows 0..ny_local+1 including the two ghost/halo rows. */
+int pm_slab_rows(pm_solver* s, int field, int* first_global_row, int* nrows, int* ncols);
+int pm_upload_slab(pm_solver* s, int field, const double* host, size_t count);
+int pm_download_slab(pm_solver* s, int field, double* host, size_t count);
 int pm_upload_mask(pm_solver* s, const uint8_t* is_fluid, size_t count);   /* step only; default is the reference rectangle */
 int pm_download_mask(pm_solver* s, uint8_t* is_fluid, size_t count);
 /* Synthetic state generated on the device: value(field, j, i) = U(-1,1) from
@@ -175,6 +180,9 @@ typedef struct pm_timing {
   int64_t ppe_passes;   /* PPE kernel passes since creation */
 } pm_timing;
 int pm_get_timing(pm_solver* s, pm_timing* t);
+/* CUDA-event stopwatch on the handle's own stream (torch.cuda.Event would only see torch's stream). */
+int pm_timer_start(pm_solver* s);
+int pm_timer_stop(pm_solver* s, double* elapsed_ms); /* synchronizes the stream */
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,91 @@
+"""CPU tests of the drop-in boundary: libpm.so loads, exports every symbol include/pm.h declares,
+its host-side logic agrees with the oracle, and it refuses to run without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pm.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(pm):
+    L = pm.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(L, s), f"libpm.so does not export {s}"
+    assert set(syms) == set(pm.EXPORTS), "pm_ctypes.EXPORTS out of sync with include/pm.h"
+    assert L.pm_abi_version() == 1
+
+
+def test_struct_layout_matches_header(pm):
+    # pm_create rejects a struct of the wrong size: a cheap ABI check that needs no GPU
+    cfg = pm.config_init(pm.CASE_CAVITY)
+    assert cfg.struct_size == C.sizeof(pm.PmConfig)
+    bad = cfg.copy()
+    bad.struct_size = 8
+    h = C.c_void_p()
+    assert pm.lib().pm_create(C.byref(bad), C.byref(h)) == 1
+    assert b"ABI mismatch" in pm.lib().pm_last_error(None)
+
+
+@pytest.mark.parametrize("case_id", [0, 1, 2])
+@pytest.mark.parametrize("args", [(0, 0, 0.0, 0.0), (128, 128, 100.0, 1e-3), (256, 64, 1000.0, 5e-4)])
+def test_config_init_matches_oracle(pm, orc, case_id, args):
+    a = pm.config_init(case_id, *args)
+    b = orc.config_init(case_id, *args)
+    for k in ("nx", "ny", "total_steps", "step_i_location", "inlet_j_max", "max_iters", "print_interval", "save_interval"):
+        assert getattr(a, k) == getattr(b, k), k
+    for k in ("dx", "dy", "nu", "dt", "u_ref", "rho", "omega", "tol_factor", "abs_tol", "lx", "ly", "re", "cfl", "final_time"):
+        assert getattr(a, k) == getattr(b, k), k
+
+
+def test_error_behaviour_mirrors_reference(pm):
+    L = pm.lib()
+    h = C.c_void_p()
+    cfg = pm.config_init(pm.CASE_CAVITY)
+    bad = cfg.copy(); bad.nx = 0
+    assert L.pm_create(C.byref(bad), C.byref(h)) == 1  # invalid_argument, cavity-01.cpp:57-59
+    assert b"Field dimensions must be positive" in L.pm_last_error(None)
+    bad = cfg.copy(); bad.dt = 0.0
+    assert L.pm_create(C.byref(bad), C.byref(h)) == 2  # runtime_error, cavity-01.cpp:423-425
+    assert b"non-positive" in L.pm_last_error(None)
+    st = pm.config_init(pm.CASE_STEP)
+    bad = st.copy(); bad.step_i_location = st.nx
+    assert L.pm_create(C.byref(bad), C.byref(h)) == 2  # backwards_step-01.cpp:459-461
+    assert b"outside computational domain" in L.pm_last_error(None)
+    assert L.pm_config_init(None, 0, 0, 0, 0.0, 0.0) == 1
+    assert L.pm_config_init(C.byref(cfg), 7, 0, 0, 0.0, 0.0) == 1
+
+
+def test_slab_ranges_tile_the_grid(pm):
+    L = pm.lib()
+    for ny, n in [(16384 * 8, 8), (31, 2), (63, 4), (10, 3)]:
+        nxt = 0
+        for r in range(n):
+            j0, nyl = C.c_int(), C.c_int()
+            assert L.pm_slab_range(ny, n, r, C.byref(j0), C.byref(nyl)) == 0
+            assert j0.value == nxt and nyl.value >= ny // n
+            nxt += nyl.value
+        assert nxt == ny
+    assert L.pm_slab_range(4, 8, 0, None, None) == 1
+
+
+def test_no_cpu_fallback(pm):
+    """Without a CUDA device the product must fail loudly, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    cfg = pm.config_init(pm.CASE_CAVITY, 16, 16)
+    h = C.c_void_p()
+    assert pm.lib().pm_create(C.byref(cfg), C.byref(h)) == 3  # PM_ERR_CUDA
+    assert b"no CPU path" in pm.lib().pm_last_error(None)
+    with pytest.raises(pm.PmError):
+        pm.Solver(cfg)

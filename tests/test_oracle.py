@@ -1,0 +1,104 @@
+"""CPU tests: the oracle (oracle/ref_cpu.cpp) against the golden vectors recorded from the
+unmodified reference, and against the reference itself when oracle/_ref is present."""
+import numpy as np
+import pytest
+
+from conftest import bits_equal, load_golden, rel_l2
+
+GOLDEN_CASES = ["cavity_default", "channel_default", "step_default", "cavity_k50_32", "channel_k50", "step_k50"]
+SLOW_GOLDEN = ["cavity_cfg0", "channel_cfg1"]
+
+
+def oracle_from_golden(orc, g):
+    case_id = int(g["case_id"])
+    # nx/ny/Re/dt are whatever the reference build was patched to; take its own derived numbers
+    cfg = orc.config_init(case_id, int(g["prm_nx"]), int(g["prm_ny"]))
+    cfg.dt = float(g["prm_dt"]); cfg.omega = float(g["prm_omega"]); cfg.nu = float(g["prm_nu"])
+    cfg.dx = float(g["prm_dx"]); cfg.dy = float(g["prm_dy"]); cfg.max_iters = int(g["prm_max_iters"])
+    cfg.ppe_method = 2  # lexicographic, the reference ordering
+    O = orc.Oracle(cfg)
+    O.apply_bc(0)  # both reference constructors / run() apply the BCs once before the loop
+    return O
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES + SLOW_GOLDEN)
+def test_oracle_reproduces_reference_bitwise(orc, name):
+    g = load_golden(name)
+    O = oracle_from_golden(orc, g)
+    for n in range(int(g["steps"])):
+        r = O.step(1)
+        assert r.iterations == int(g["iters"][n])
+        assert r.residual == float(g["res"][n])
+    for fid in range(6):
+        assert bits_equal(O.field(fid), g[f"f{fid}"]), f"{name} field {fid}"
+    assert np.array_equal(O.mask(), g["mask"])
+
+
+@pytest.mark.parametrize("case_id,name", [(0, "cavity_default"), (1, "channel_default"), (2, "step_default")])
+def test_parameter_derivation_matches_reference(orc, case_id, name):
+    g = load_golden(name)
+    cfg = orc.config_init(case_id)
+    for k in ("nx", "ny", "total_steps", "max_iters"):
+        assert getattr(cfg, k) == int(g[f"prm_{k}"]), k
+    for k in ("dt", "omega", "nu", "dx", "dy"):
+        assert getattr(cfg, k) == float(g[f"prm_{k}"]), k
+
+
+def test_known_banner_values(orc):
+    # "dt=0.007937, steps=2520", "Relaxation factor=1.906455" etc.
+    c = orc.config_init(0)
+    assert f"{c.dt:.6f}" == "0.007937" and c.total_steps == 2520 and f"{c.omega:.6f}" == "1.906455"
+    c = orc.config_init(1)
+    assert f"{c.dt:.6f}" == "0.006504" and c.total_steps == 1537 and f"{c.omega:.6f}" == "1.863488"
+    c = orc.config_init(2)
+    assert f"{c.dt:.6f}" == "0.004883" and c.total_steps == 3072 and f"{c.omega:.6f}" == "1.873001"
+    assert c.step_i_location == 64 and c.inlet_j_max == 16
+    O = orc.Oracle(c)
+    assert int(O.mask()[1:-1, 1:-1].sum()) == 7168  # "Fluid cells: 7168/8192"
+
+
+@pytest.mark.parametrize("name", ["cavity_default", "channel_default", "step_default"])
+def test_oracle_phases_match_reference_on_random_fields(orc, name):
+    """Phase by phase on seeded random input, against the reference's own member functions."""
+    if not orc.ref_available(name):
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    R = orc.Reference(name)
+    cfg = orc.config_init(R.case_id)
+    cfg.ppe_method = 2
+    cfg.max_iters = 10000
+    O = orc.Oracle(cfg)
+    O.fill_random(1234)
+    for fid in range(6):
+        R.set(fid, O.field(fid))
+    O.apply_bc(0); R.apply_bc(0)
+    O.predict(); R.predict()
+    if R.case_id != 0:
+        O.apply_bc(1); R.apply_bc(1)
+    O.source(); R.source()
+    if R.case_id != 0:
+        assert bits_equal(O.field(5), R.get(5))
+    ro = O.ppe_solve(); it, res = R.ppe()
+    assert (ro.iterations, ro.residual) == (it, res)
+    O.correct(); R.correct()
+    for fid in range(6):
+        assert bits_equal(O.field(fid), R.get(fid)), f"{name} field {fid}"
+
+
+@pytest.mark.parametrize("case_id", [0, 1, 2])
+def test_orderings_converge_to_the_same_field(orc, case_id):
+    """Red-black and lexicographic SOR, both run to the reference tolerance, agree to the
+    north-star bound (1e-6 relative L2); Jacobi at omega=1 is checked for self-consistency only."""
+    nx, ny = (24, 24) if case_id == 0 else (48, 16)
+    fields = {}
+    for method in (2, 1):
+        cfg = orc.config_init(case_id, nx, ny)
+        if case_id == 2:
+            cfg.step_i_location, cfg.inlet_j_max = 12, 8
+        cfg.ppe_method = method
+        cfg.max_iters = 100000
+        O = orc.Oracle(cfg)
+        O.apply_bc(0)
+        O.step(5)
+        fields[method] = [O.field(f).copy() for f in range(3)]
+    for a, b in zip(fields[1], fields[2]):
+        assert rel_l2(a, b) < 1e-6
