@@ -136,7 +136,7 @@ static void fill_kp(pm_solver* s, int j0, int nyl) {
   std::memset(&k, 0, sizeof k);
   k.nx = c.nx; k.ny = c.ny; k.nyl = nyl; k.j0 = j0;
   // pitch: PM_OFFC left pad + nx+2 columns + right pad for tile halos, rounded to 16 doubles (128 B)
-  k.pitch = ((PM_OFFC + c.nx + 2 + PM_PADR + 15) / 16) * 16;
+  k.pitch = std::max(144, ((PM_OFFC + c.nx + 2 + PM_PADR + 15) / 16) * 16);
   k.padr = PM_PADR;
   k.case_id = c.case_id;
   k.has_mask = c.case_id == PM_CASE_STEP;
@@ -264,7 +264,7 @@ static int create_impl(pm_solver* s, const pm_config* cfg) {
                               (c.kernel_path == PM_PATH_AUTO && size_t(c.nx) * size_t(nyl) >= (size_t(1) << 18)));
   if (s->use_tiled) {
     std::string e;
-    if (!tiled_create(&s->tiled, c, k, s->pl[PL_P0], s->pl[PL_P1], s->pl[PL_F], s->rows_alloc, &e))
+    if (!tiled_create(&s->tiled, c, k, s->pl[PL_P0], s->pl[PL_P1], s->rows_alloc, &e))
       return fail(s, PM_ERR_CUDA, "tiled path setup: %s", e.c_str());
     s->sweeps = s->tiled.sweeps;
   }
@@ -424,7 +424,9 @@ extern "C" int pm_fill_zero(pm_solver* s) {
   s->f_max_valid = false;
   return PM_OK;
 }
-extern "C" int pm_fill_random(pm_solver* s, uint64_t seed) {
+extern "C" int pm_fill_random_scaled(pm_solver* s, uint64_t seed, double amplitude);
+extern "C" int pm_fill_random(pm_solver* s, uint64_t seed) { return pm_fill_random_scaled(s, seed, 1.0); }
+extern "C" int pm_fill_random_scaled(pm_solver* s, uint64_t seed, double amplitude) {
   if (!s) return PM_ERR_INVALID_ARGUMENT;
   CK(cudaSetDevice(s->device));
   PMTRY(pm_fill_zero(s));
@@ -433,7 +435,7 @@ extern "C" int pm_fill_random(pm_solver* s, uint64_t seed) {
     int rows, cols;
     field_dims(s, field, &rows, &cols);
     const dim3 b(128, 4), g((cols + 127) / 128, (k.nyl + 2 + 3) / 4);
-    k_fill_random<<<g, b, 0, s->stream>>>(k, field_plane(s, field), field, rows, cols, seed);
+    k_fill_random<<<g, b, 0, s->stream>>>(k, field_plane(s, field), field, rows, cols, seed, amplitude);
     CKL(s);
   }
   s->f_max_valid = false;
@@ -599,14 +601,67 @@ static int launch_iteration_simple(pm_solver* s, int krel, int kabs) {
   return cav ? launch_iteration_simple<Fast, 0>(s, krel, kabs) : launch_iteration_simple<Fast, 1>(s, krel, kabs);
 }
 
-static int tiled_solve(pm_solver* s, int* iters, double* res) {
-  (void)iters; (void)res;
-  return fail(s, PM_ERR_UNSUPPORTED, "tiled path not built");
-}
-
 static int read_state(pm_solver* s) {
   CK(cudaMemcpyAsync(s->h_state, s->d_state, sizeof(PpeState), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
+  return PM_OK;
+}
+
+
+// Tiled path: pass n reads buffer in0 ^ (n & 1) holding iterate n*T and writes iterate n*T + nsw to the
+// other buffer.  The loop test runs on the device (tiled_stop); the host only polls the sticky flag.
+static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
+  const KP& k = s->kp;
+  const TiledPlan& pl = s->tiled;
+  const int K = s->cfg.max_iters, T = pl.sweeps;
+  const int in0 = s->p_cur == PL_P0 ? 0 : 1;
+  int m = 0, n = 0;
+  bool done = false;
+  int chunk = s->cfg.poll_chunk > 0 ? s->cfg.poll_chunk : std::max(4, std::min(128, s->last_iters / (8 * T)));
+  while (m < K && !done) {
+    int launched = 0;
+    while (m < K && launched < chunk) {
+      const int nsw = std::min(T, K - m);
+      CK(tiled_launch(&pl, k, in0 ^ (n & 1), s->pl[PL_F], s->d_state, s->d_res, m, nsw, 0, 0, pl.tiles_y, s->stream));
+      s->timing.kernel_launches++;
+      s->timing.ppe_passes++;
+      m += nsw; ++n; ++launched;
+    }
+    PMTRY(read_state(s));
+    done = s->h_state->done != 0;
+    if (s->cfg.poll_chunk <= 0) chunk = std::min(128, chunk * 2);
+  }
+  if (!done) {  // residual of the last iterate (and the loop test for the iterates of the last pass)
+    CK(tiled_launch(&pl, k, in0 ^ (n & 1), s->pl[PL_F], s->d_state, s->d_res, m, 0, 0, 0, pl.tiles_y, s->stream));
+    s->timing.kernel_launches++;
+    s->timing.ppe_passes++;
+    PMTRY(read_state(s));
+    done = s->h_state->done != 0;
+  }
+  int iters, buf;
+  if (done) {
+    iters = s->h_state->iters;
+    const int nb = iters / T, mb = nb * T;
+    buf = in0 ^ (nb & 1);
+    if (iters > mb) {  // land on the exact iterate: replay the first iters-mb sweeps of that pass
+      CK(tiled_launch(&pl, k, buf, s->pl[PL_F], s->d_state, s->d_res, mb, iters - mb, 1, 0, pl.tiles_y, s->stream));
+      s->timing.kernel_launches++;
+      s->timing.ppe_passes++;
+      buf ^= 1;
+    }
+  } else {
+    iters = K;
+    buf = in0 ^ (n & 1);
+  }
+  s->p_cur = buf ? PL_P1 : PL_P0;
+  if (iters >= 1) {
+    CK(cudaMemcpyAsync(s->h_res, s->d_res + iters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    std::memcpy(res_out, s->h_res, 8);
+  } else {
+    *res_out = s->h_state->res_init;
+  }
+  *iters_out = iters;
   return PM_OK;
 }
 

@@ -481,11 +481,11 @@ __global__ void k_copy_corners(const __grid_constant__ KP k, const double* __res
 // ---------------------------------------------------------------------------
 // value(field, j, i) keyed by the reference flat index j*cols + i with GLOBAL j.
 __global__ void k_fill_random(const __grid_constant__ KP k, double* __restrict__ a, int field, int rows_global,
-                              int cols, uint64_t seed) {
+                              int cols, uint64_t seed, double amplitude) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int jl = blockIdx.y * blockDim.y + threadIdx.y;  // local rows 0..nyl+1
   if (i >= cols || jl > k.nyl + 1) return;
   const int j = k.j0 + jl;
   if (j >= rows_global) return;
-  a[pm_idx(k, jl, i)] = pm_synth(seed, field, uint64_t(j) * uint64_t(cols) + uint64_t(i));
+  a[pm_idx(k, jl, i)] = __dmul_rn(amplitude, pm_synth(seed, field, uint64_t(j) * uint64_t(cols) + uint64_t(i)));
 }

@@ -1,8 +1,467 @@
-// pm_kernels_tiled.cuh — placeholder until the TMA-staged tiled pressure sweep lands.
+// pm_kernels_tiled.cuh — the bandwidth path of the pressure solve for large unmasked grids.
+//
+// One launch ("pass") advances the pressure field by up to T sweeps (temporal blocking) and
+// produces the infinity-norm residual of every iterate it passes through, moving p once in and
+// once out of HBM and f once in:
+//   * the (TY+2H) x 128 tile of p around a (TY x TX) output block is staged into shared memory by
+//     ONE TMA tensor load (cp.async.bulk.tensor.2d, zero-filled outside the allocation) signalled
+//     on an mbarrier; f goes straight from HBM into registers with 128-bit row loads meanwhile;
+//   * every thread keeps its RPT x 2 cells of p and f in registers for the whole pass; shared
+//     memory only carries the values neighbouring threads exchange (one 64-bit load and one
+//     64-bit store per cell update), so the sweeps are bounded by the FP64 pipe, not by smem;
+//   * halo H = 2T (red-black: one ring per colour half-sweep) or T (Jacobi): cells closer than s
+//     rings to the tile edge are stale after s half-sweeps and are never written back;
+//   * residuals cost no extra loads: a Jacobi or red update reads exactly the operands of the
+//     residual of the iterate it replaces; a black update's operands are the residual operands of
+//     the iterate it creates (reference residual trees: cavity-01.cpp:664-673, channel-01.cpp:676-678);
+//   * the output block is written with 128-bit stores; wall ghosts (channel form) are refreshed by
+//     the thread that owns the wall-adjacent cell, in the tile and in HBM (channel-01.cpp:531-541).
+// The reference's loop test (cavity-01.cpp:635) is evaluated on the device at the start of every
+// pass from the residuals of the previous pass; passes after convergence exit at once and leave
+// both buffers untouched, and the host re-runs at most one partial pass to land on the exact iterate.
 #pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
 #include <string>
+
 #include "pm_common.cuh"
-struct TiledPlan { int sweeps = 1; };
-static inline bool tiled_supported(const pm_config&, const KP&) { return false; }
-static inline bool tiled_create(TiledPlan*, const pm_config&, const KP&, double*, double*, double*, int, std::string* e) { *e = "not built"; return false; }
+
+#define PM_TILE_THREADS 256
+
+template <int METHOD, int T>
+struct TileCfg {
+  static constexpr int H = (METHOD == PM_PPE_SOR_RB) ? 2 * T : ((T + 1) / 2) * 2;  // even: keeps 16-byte alignment of row pairs
+  static constexpr int SW = 128;                  // tile width in doubles == 64 column pairs == one TMA box row (1 KiB)
+  static constexpr int NSEG = PM_TILE_THREADS / 64;
+  static constexpr int RPT = 10;                  // rows per thread
+  static constexpr int SH = NSEG * RPT;           // tile height
+  static constexpr int TX = SW - 2 * H;           // output block
+  static constexpr int TY = SH - 2 * H;
+  static constexpr int SMEM_BYTES = SH * SW * 8;
+  static_assert(TX > 0 && TY > 0, "halo too deep for the tile");
+  static_assert(H <= PM_PADR, "halo deeper than the pad rows of the planes");
+};
+
+// ---- mbarrier / TMA primitives (sm_90+ PTX; SASS: SYNCS.*, UTMALDG) -----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int cx, int cy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(cx), "r"(cy)
+      : "memory");
+}
+
+// Loop test of the reference for the pass that starts at iterate m0: has any iterate of the
+// previous pass (m0-T .. m0-1) met the tolerance?  Returns the first such iterate in *first.
+__device__ __forceinline__ bool tiled_stop(const PpeState* st, const unsigned long long* res_bits, int m0, int T, int* first) {
+  if (st->done) { *first = -1; return true; }
+  const int lo = max(1, m0 - T);
+  for (int m = lo; m < m0; ++m) {
+    const double r = __longlong_as_double((long long)res_bits[m]);
+    if (!(r > st->tol)) { *first = m; return true; }
+  }
+  return false;
+}
+
+template <class A, int FORM>
+__device__ __forceinline__ double cell_update(const KP& k, int j, int i, double pc, double pe, double pw, double pn, double ps, double f) {
+  if (FORM == 0) return upd_cavity<A>(k, j, i, pc, pe, pw, pn, ps, f);
+  return upd_channel<A>(k, pc, pe, pw, pn, ps, f);
+}
+template <class A, int FORM>
+__device__ __forceinline__ double cell_residual(const KP& k, int j, int i, double pc, double pe, double pw, double pn, double ps, double f) {
+  if (FORM == 0) return res_cavity<A>(k, j, i, pc, pe, pw, pn, ps, f, k.idx2);
+  return res_channel<A>(k, pc, pe, pw, pn, ps, f);
+}
+
+// Per-thread view of the tile.
+template <int RPT>
+struct Cells {
+  double p0[RPT], p1[RPT], f0[RPT], f1[RPT];
+};
+
+// One colour half-sweep (red-black) over the thread's rows.  PX: the target of row r is the .x cell
+// iff (r & 1) == PX.  PRE: accumulate the residual of the iterate being replaced (operands before
+// the update) ; POST: of the iterate being created (operands after).  commit=false: residual only.
+template <class A, int FORM, class C, int PX, bool PRE, bool POST>
+__device__ __forceinline__ void rb_half(const KP& k, double* __restrict__ tile, Cells<C::RPT>& c, int rr0, int c0, int i0, int jg0,
+                                        unsigned mW, unsigned mO, bool colW0, bool colW1, bool colO0, bool colO1, bool commit,
+                                        double& rmax_pre, double& rmax_post) {
+  constexpr int SW = C::SW, SH = C::SH, RPT = C::RPT;
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const bool tx = (r & 1) == PX;  // compile-time after unrolling
+    const int rr = rr0 + r;
+    const int j = jg0 + r;
+    const int col = tx ? c0 : c0 + 1;
+    const int i = tx ? i0 : i0 + 1;
+    const double pc = tx ? c.p0[r] : c.p1[r];
+    const double fc = tx ? c.f0[r] : c.f1[r];
+    double pw, pe, pn, ps;
+    if (tx) {
+      pw = tile[rr * SW + max(col - 1, 0)];
+      pe = c.p1[r];
+    } else {
+      pw = c.p0[r];
+      pe = tile[rr * SW + min(col + 1, SW - 1)];
+    }
+    if (r + 1 < RPT) pn = tx ? c.p0[r + 1] : c.p1[r + 1];
+    else pn = tile[min(rr + 1, SH - 1) * SW + col];
+    if (r >= 1) ps = tx ? c.p0[r - 1] : c.p1[r - 1];
+    else ps = tile[max(rr - 1, 0) * SW + col];
+    const bool rowW = (mW >> r) & 1u, rowO = (mO >> r) & 1u;
+    const bool upd = commit && rowW && (tx ? colW0 : colW1);
+    const bool out = rowO && (tx ? colO0 : colO1);
+    if (PRE) {
+      const double rs = cell_residual<A, FORM>(k, j, i, pc, pe, pw, pn, ps, fc);
+      if (out) rmax_pre = fmax(rmax_pre, fabs(rs));
+    }
+    const double nv = cell_update<A, FORM>(k, j, i, pc, pe, pw, pn, ps, fc);
+    if (upd) {
+      if (tx) c.p0[r] = nv; else c.p1[r] = nv;
+      tile[rr * SW + col] = nv;
+      if (FORM == 1) {  // refresh the wall ghosts this cell owns (channel-01.cpp:531-541)
+        if (i == 1) { pw = nv; tile[rr * SW + col - 1] = nv; }
+        if (i == k.nx) {
+          pe = 0.0;
+          tile[rr * SW + col + 1] = 0.0;
+          if (tx) c.p1[r] = 0.0;
+        }
+        if (j == 1) {
+          ps = nv;
+          tile[(rr - 1) * SW + col] = nv;
+          if (r >= 1) { if (tx) c.p0[r - 1] = nv; else c.p1[r - 1] = nv; }
+        }
+        if (j == k.ny) {
+          pn = nv;
+          tile[(rr + 1) * SW + col] = nv;
+          if (r + 1 < RPT) { if (tx) c.p0[r + 1] = nv; else c.p1[r + 1] = nv; }
+        }
+      }
+      if (POST) {
+        const double rs = cell_residual<A, FORM>(k, j, i, nv, pe, pw, pn, ps, fc);
+        if (out) rmax_post = fmax(rmax_post, fabs(rs));
+      }
+    }
+  }
+}
+
+// One Jacobi sweep: new values of both cells of every row from the previous iterate, staged in
+// registers until every thread has finished reading.
+template <class A, int FORM, class C>
+__device__ __forceinline__ void jacobi_sweep(const KP& k, double* __restrict__ tile, Cells<C::RPT>& c, int rr0, int c0, int i0, int jg0,
+                                             unsigned mW, unsigned mO, bool colW0, bool colW1, bool colO0, bool colO1, bool commit,
+                                             double& rmax_pre) {
+  constexpr int SW = C::SW, SH = C::SH, RPT = C::RPT;
+  double n0[RPT], n1[RPT];
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const int rr = rr0 + r, j = jg0 + r;
+    const double wl = tile[rr * SW + max(c0 - 1, 0)];
+    const double er = tile[rr * SW + min(c0 + 2, SW - 1)];
+    double pn0, pn1, ps0, ps1;
+    if (r + 1 < RPT) { pn0 = c.p0[r + 1]; pn1 = c.p1[r + 1]; }
+    else { const double2 t = *reinterpret_cast<const double2*>(&tile[min(rr + 1, SH - 1) * SW + c0]); pn0 = t.x; pn1 = t.y; }
+    if (r >= 1) { ps0 = c.p0[r - 1]; ps1 = c.p1[r - 1]; }
+    else { const double2 t = *reinterpret_cast<const double2*>(&tile[max(rr - 1, 0) * SW + c0]); ps0 = t.x; ps1 = t.y; }
+    const bool rowO = (mO >> r) & 1u;
+    const double r0v = cell_residual<A, FORM>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0[r]);
+    const double r1v = cell_residual<A, FORM>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1[r]);
+    if (rowO && colO0) rmax_pre = fmax(rmax_pre, fabs(r0v));
+    if (rowO && colO1) rmax_pre = fmax(rmax_pre, fabs(r1v));
+    n0[r] = cell_update<A, FORM>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0[r]);
+    n1[r] = cell_update<A, FORM>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1[r]);
+  }
+  if (!commit) return;  // uniform across the block
+  __syncthreads();      // every neighbour value of the old iterate has been read
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const int rr = rr0 + r, j = jg0 + r;
+    const bool rowW = (mW >> r) & 1u;
+    if (rowW && colW0) {
+      c.p0[r] = n0[r];
+      tile[rr * SW + c0] = n0[r];
+    }
+    if (rowW && colW1) {
+      c.p1[r] = n1[r];
+      tile[rr * SW + c0 + 1] = n1[r];
+    }
+    if (FORM == 1 && rowW) {  // wall ghosts from the new values
+      if (colW0 && i0 == 1) tile[rr * SW + c0 - 1] = n0[r];
+      if (colW0 && i0 == k.nx) { tile[rr * SW + c0 + 1] = 0.0; c.p1[r] = 0.0; }
+      if (colW1 && i0 + 1 == k.nx) tile[rr * SW + c0 + 2] = 0.0;
+    }
+  }
+  if (FORM == 1) {
+    // row ghosts: after all new values are in place (a ghost row register may belong to this thread)
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int rr = rr0 + r, j = jg0 + r;
+      const bool rowW = (mW >> r) & 1u;
+      if (!rowW) continue;
+      if (j == 1) {
+        if (colW0) { tile[(rr - 1) * SW + c0] = n0[r]; if (r >= 1) c.p0[r - 1] = n0[r]; }
+        if (colW1) { tile[(rr - 1) * SW + c0 + 1] = n1[r]; if (r >= 1) c.p1[r - 1] = n1[r]; }
+      }
+      if (j == k.ny) {
+        if (colW0) { tile[(rr + 1) * SW + c0] = n0[r]; if (r + 1 < RPT) c.p0[r + 1] = n0[r]; }
+        if (colW1) { tile[(rr + 1) * SW + c0 + 1] = n1[r]; if (r + 1 < RPT) c.p1[r + 1] = n1[r]; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <class A, int FORM, int METHOD, int T>
+__global__ void __launch_bounds__(PM_TILE_THREADS, 2)
+    k_ppe_tiled(const __grid_constant__ KP k, const __grid_constant__ CUtensorMap tmap_in, double* __restrict__ pout,
+                const double* __restrict__ f, PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits, int m0,
+                int nsw, int force, int tile_row0) {
+  using C = TileCfg<METHOD, T>;
+  constexpr int H = C::H, SW = C::SW, SH = C::SH, RPT = C::RPT, TX = C::TX, TY = C::TY;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  double* tile = reinterpret_cast<double*>(smem_raw);
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ double red[(T + 1) * 8];
+
+  const int tid = threadIdx.x;
+  if (!force) {
+    int first = -1;
+    if (tiled_stop(st, res_bits, m0, T, &first)) {
+      if (first >= 0 && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+        st->iters = first;
+        st->done = 1;
+      }
+      return;
+    }
+  }
+  const int bx = blockIdx.x, by = blockIdx.y + tile_row0;
+  const int x0 = 1 + bx * TX, y0 = 1 + by * TY;  // first output cell (i, jl)
+  const int ib = x0 - H, jb = y0 - H;            // tile origin (i, jl)
+
+  if (tid == 0) {
+    mbar_init(&mbar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&mbar, C::SMEM_BYTES);
+    tma_load_2d(tile, &tmap_in, &mbar, PM_OFFC + ib, k.padr + jb);
+  }
+
+  const int q = tid & 63, sg = tid >> 6;
+  const int c0 = 2 * q, i0 = ib + c0;
+  const int rr0 = sg * RPT;
+  const int jl0 = jb + rr0, jg0 = k.j0 + jl0;
+  const bool colI0 = i0 >= 1 && i0 <= k.nx, colI1 = i0 + 1 >= 1 && i0 + 1 <= k.nx;
+  const bool colW0 = colI0 && c0 >= 1, colW1 = colI1 && c0 + 1 <= SW - 2;
+  const bool colO0 = colI0 && c0 >= H && c0 < H + TX, colO1 = colI1 && c0 + 1 >= H && c0 + 1 < H + TX;
+  unsigned mW = 0, mO = 0, mI = 0;
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const int rr = rr0 + r, jl = jl0 + r, j = jg0 + r;
+    const bool rowI = j >= 1 && j <= k.ny && jl >= 1 - H && jl <= k.nyl + H;
+    if (rowI) mI |= 1u << r;
+    if (rowI && rr >= 1 && rr <= SH - 2) mW |= 1u << r;
+    if (jl >= 1 && jl <= k.nyl && rr >= H && rr < H + TY) mO |= 1u << r;
+  }
+
+  // f: HBM -> registers, 128-bit row loads, overlapping the TMA transfer of p
+  Cells<RPT> c;
+  {
+    const double* fp = f + pm_idx(k, jl0, i0);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const bool rowI = (mI >> r) & 1u;
+      double2 v = make_double2(0.0, 0.0);
+      if (rowI && colI0 && colI1) v = __ldg(reinterpret_cast<const double2*>(fp + size_t(r) * k.pitch));
+      else if (rowI && colI0) v.x = __ldg(fp + size_t(r) * k.pitch);
+      else if (rowI && colI1) v.y = __ldg(fp + size_t(r) * k.pitch + 1);
+      c.f0[r] = v.x;
+      c.f1[r] = v.y;
+    }
+  }
+  mbar_wait(&mbar, 0);
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const double2 v = *reinterpret_cast<const double2*>(&tile[(rr0 + r) * SW + c0]);
+    c.p0[r] = v.x;
+    c.p1[r] = v.y;
+  }
+
+  double rm[T + 1];
+#pragma unroll
+  for (int t = 0; t <= T; ++t) rm[t] = 0.0;
+
+  const int par0 = (i0 + jg0) & 1;  // colour of the .x cell of row 0; uniform over the warp
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    if (t < nsw || (t == 0 && nsw == 0)) {
+      const bool commit = t < nsw;
+      if (METHOD == PM_PPE_SOR_RB) {
+        // colour 0 first ((i + j) even), as the oracle's red-black restatement
+        if (par0 == 0) rb_half<A, FORM, C, 0, true, false>(k, tile, c, rr0, c0, i0, jg0, mW, mO, colW0, colW1, colO0, colO1, commit, rm[t], rm[t + 1]);
+        else rb_half<A, FORM, C, 1, true, false>(k, tile, c, rr0, c0, i0, jg0, mW, mO, colW0, colW1, colO0, colO1, commit, rm[t], rm[t + 1]);
+        if (commit) {
+          __syncthreads();
+          if (par0 == 0) rb_half<A, FORM, C, 1, false, true>(k, tile, c, rr0, c0, i0, jg0, mW, mO, colW0, colW1, colO0, colO1, true, rm[t], rm[t + 1]);
+          else rb_half<A, FORM, C, 0, false, true>(k, tile, c, rr0, c0, i0, jg0, mW, mO, colW0, colW1, colO0, colO1, true, rm[t], rm[t + 1]);
+          __syncthreads();
+        }
+      } else {
+        jacobi_sweep<A, FORM, C>(k, tile, c, rr0, c0, i0, jg0, mW, mO, colW0, colW1, colO0, colO1, commit, rm[t]);
+      }
+    }
+  }
+
+  // ---- write the output block: 128-bit stores, plus the wall ghosts its cells own ----
+  if (nsw > 0) {
+    double* op = pout + pm_idx(k, jl0, i0);
+    const int P = k.pitch;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      if (!((mO >> r) & 1u)) continue;
+      double* o = op + size_t(r) * P;
+      if (colO0 && colO1) *reinterpret_cast<double2*>(o) = make_double2(c.p0[r], c.p1[r]);
+      else if (colO0) o[0] = c.p0[r];
+      else if (colO1) o[1] = c.p1[r];
+      if (FORM == 1) {
+        const int j = jg0 + r;
+        if (colO0 && i0 == 1) o[-1] = c.p0[r];
+        if (colO0 && i0 == k.nx) o[1] = 0.0;
+        if (colO1 && i0 + 1 == k.nx) o[2] = 0.0;
+        if (j == 1) { if (colO0) o[-P] = c.p0[r]; if (colO1) o[1 - P] = c.p1[r]; }
+        if (j == k.ny) { if (colO0) o[P] = c.p0[r]; if (colO1) o[1 + P] = c.p1[r]; }
+      }
+    }
+  }
+
+  // ---- residual norms: warp shuffles, block tree, one atomic per iterate ----
+  const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+  for (int t = 0; t <= T; ++t) {
+    const double v = warp_max(rm[t]);
+    if (lane == 0) red[t * 8 + w] = v;
+  }
+  __syncthreads();
+  if (tid <= T) {
+    double v = 0.0;
+#pragma unroll
+    for (int q2 = 0; q2 < PM_TILE_THREADS / 32; ++q2) v = fmax(v, red[tid * 8 + q2]);
+    const int m = m0 + tid;
+    // Jacobi: rm[t] is the full residual of iterate m0+t (t < max(nsw,1)).  Red-black: rm[t] holds the
+    // red part of iterate m0+t and the black part of the same iterate written by sweep t (rm[t] <- POST of sweep t-1).
+    if (m >= 1 && m <= k.max_iters) atomic_max_nonneg(&res_bits[m], v);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct TiledPlan {
+  int sweeps = 1;       // T
+  int halo = 2;         // H
+  int tx = 0, ty = 0;   // output block
+  int tiles_x = 0, tiles_y = 0;
+  int smem_bytes = 0;
+  CUtensorMap map[2];   // p ping / p pong
+  double* p[2] = {nullptr, nullptr};
+  const void* kernel = nullptr;
+};
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline bool tiled_supported(const pm_config& c, const KP& k) {
+  if (c.case_id == PM_CASE_STEP) return false;  // the obstacle mask stays on the general path
+  if (c.ppe_method != PM_PPE_JACOBI && c.ppe_method != PM_PPE_SOR_RB) return false;
+  if (k.pitch < 128) return false;
+  return true;
+}
+
+template <class A, int FORM, int METHOD, int T>
+static const void* tiled_kernel_ptr() { return reinterpret_cast<const void*>(&k_ppe_tiled<A, FORM, METHOD, T>); }
+
+template <int METHOD, int T>
+static void tiled_geometry(TiledPlan* pl) {
+  using C = TileCfg<METHOD, T>;
+  pl->sweeps = T; pl->halo = C::H; pl->tx = C::TX; pl->ty = C::TY; pl->smem_bytes = C::SMEM_BYTES;
+}
+
+template <class A, int FORM>
+static const void* tiled_pick(int method, int T, TiledPlan* pl) {
+  if (method == PM_PPE_SOR_RB) {
+    switch (T) {
+      case 1: tiled_geometry<PM_PPE_SOR_RB, 1>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 1>();
+      case 2: tiled_geometry<PM_PPE_SOR_RB, 2>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 2>();
+      case 3: tiled_geometry<PM_PPE_SOR_RB, 3>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 3>();
+    }
+  } else {
+    switch (T) {
+      case 1: tiled_geometry<PM_PPE_JACOBI, 1>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 1>();
+      case 2: tiled_geometry<PM_PPE_JACOBI, 2>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 2>();
+      case 4: tiled_geometry<PM_PPE_JACOBI, 4>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 4>();
+    }
+  }
+  return nullptr;
+}
+
+static inline bool tiled_create(TiledPlan* pl, const pm_config& c, const KP& k, double* p0, double* p1, int rows_alloc, std::string* err) {
+  int T = c.sweeps_per_pass > 0 ? c.sweeps_per_pass : 2;
+  const bool cav = c.case_id == PM_CASE_CAVITY;
+  const void* kern = nullptr;
+  if (c.exact_arith) kern = cav ? tiled_pick<Exact, 0>(c.ppe_method, T, pl) : tiled_pick<Exact, 1>(c.ppe_method, T, pl);
+  else kern = cav ? tiled_pick<Fast, 0>(c.ppe_method, T, pl) : tiled_pick<Fast, 1>(c.ppe_method, T, pl);
+  if (!kern) { *err = "sweeps_per_pass " + std::to_string(T) + " not built for this method (red-black: 1,2,3; jacobi: 1,2,4)"; return false; }
+  pl->kernel = kern;
+  pl->tiles_x = (k.nx + pl->tx - 1) / pl->tx;
+  pl->tiles_y = (k.nyl + pl->ty - 1) / pl->ty;
+  pl->p[0] = p0; pl->p[1] = p1;
+
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) { *err = "cuTensorMapEncodeTiled not available from the driver"; return false; }
+  PFN_tmapEncodeTiled encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
+  for (int b = 0; b < 2; ++b) {
+    const cuuint64_t gdim[2] = {cuuint64_t(k.pitch), cuuint64_t(rows_alloc)};
+    const cuuint64_t gstr[1] = {cuuint64_t(k.pitch) * 8};
+    const cuuint32_t box[2] = {128u, cuuint32_t(TileCfg<0, 1>::SH)};
+    const cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = encode(&pl->map[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, pl->p[b], gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)); return false; }
+  }
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes);
+  if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return false; }
+  return true;
+}
 static inline void tiled_destroy(TiledPlan*) {}
+
+// Launch one pass: reads iterate m0 from buffer `in`, writes iterate m0+nsw to the other buffer.
+static inline cudaError_t tiled_launch(const TiledPlan* pl, const KP& k, int in, const double* f, PpeState* st, unsigned long long* res,
+                                       int m0, int nsw, int force, int tile_row0, int tile_rows, cudaStream_t stream) {
+  double* pout = pl->p[in ^ 1];
+  void* args[] = {(void*)&k, (void*)&pl->map[in], (void*)&pout, (void*)&f, (void*)&st, (void*)&res,
+                  (void*)&m0, (void*)&nsw, (void*)&force, (void*)&tile_row0};
+  return cudaLaunchKernel(pl->kernel, dim3(pl->tiles_x, tile_rows), dim3(PM_TILE_THREADS), args, size_t(pl->smem_bytes), stream);
+}

@@ -61,7 +61,7 @@ def field_shape(field, nx, ny):
 EXPORTS = [
     "pm_config_init", "pm_slab_range", "pm_create", "pm_destroy", "pm_last_error", "pm_status_string",
     "pm_abi_version", "pm_nccl_unique_id", "pm_upload", "pm_download", "pm_slab_rows", "pm_upload_slab", "pm_download_slab", "pm_upload_mask", "pm_download_mask",
-    "pm_fill_random", "pm_fill_zero", "pm_apply_bc", "pm_predict", "pm_source", "pm_ppe_solve", "pm_correct",
+    "pm_fill_random", "pm_fill_random_scaled", "pm_fill_zero", "pm_apply_bc", "pm_predict", "pm_source", "pm_ppe_solve", "pm_correct",
     "pm_step", "pm_diagnostics", "pm_sync", "pm_get_timing", "pm_timer_start", "pm_timer_stop",
 ]
 
@@ -94,6 +94,7 @@ def lib():
     L.pm_upload_mask.argtypes = [vp, C.POINTER(C.c_uint8), C.c_size_t]
     L.pm_download_mask.argtypes = [vp, C.POINTER(C.c_uint8), C.c_size_t]
     L.pm_fill_random.argtypes = [vp, C.c_uint64]
+    L.pm_fill_random_scaled.argtypes = [vp, C.c_uint64, C.c_double]
     L.pm_fill_zero.argtypes = [vp]
     L.pm_apply_bc.argtypes = [vp, C.c_int]
     for n in ("pm_predict", "pm_source", "pm_correct", "pm_sync"):
@@ -167,8 +168,8 @@ class Solver:
         self._ck(lib().pm_download_mask(self._h, out.ctypes.data_as(C.POINTER(C.c_uint8)), out.size))
         return out
 
-    def fill_random(self, seed):
-        self._ck(lib().pm_fill_random(self._h, seed))
+    def fill_random(self, seed, amplitude=1.0):
+        self._ck(lib().pm_fill_random_scaled(self._h, seed, amplitude))
 
     def fill_zero(self):
         self._ck(lib().pm_fill_zero(self._h))

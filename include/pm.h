@@ -151,6 +151,8 @@ int pm_download_mask(pm_solver* s, uint8_t* is_fluid, size_t count);
 /* Synthetic state generated on the device: value(field, j, i) = U(-1,1) from
  * splitmix64(seed, field, flat reference index).  Same generator in oracle/. */
 int pm_fill_random(pm_solver* s, uint64_t seed);
+/* Same, scaled: value = amplitude * U(-1,1).  A power-of-two amplitude keeps host and device bit-identical. */
+int pm_fill_random_scaled(pm_solver* s, uint64_t seed, double amplitude);
 int pm_fill_zero(pm_solver* s);
 
 /* ---- phases (one per reference member function) ------------------------ */

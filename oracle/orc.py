@@ -46,6 +46,7 @@ def orc_lib():
         L.orc_field_count.argtypes = [vp, C.c_int]; L.orc_field_count.restype = C.c_size_t
         L.orc_mask.argtypes = [vp]; L.orc_mask.restype = C.POINTER(C.c_uint8)
         L.orc_fill_random.argtypes = [vp, C.c_uint64]
+        L.orc_fill_random_scaled.argtypes = [vp, C.c_uint64, C.c_double]
         L.orc_synth.argtypes = [C.c_uint64, C.c_int, C.c_uint64]; L.orc_synth.restype = C.c_double
         L.orc_apply_bc.argtypes = [vp, C.c_int]
         L.orc_predict.argtypes = [vp]
@@ -100,7 +101,7 @@ class Oracle:
     def set_method(self, m): self.L.orc_set_method(self.h, m)
     def set_max_iters(self, k): self.L.orc_set_max_iters(self.h, k)
     def set_omega(self, w): self.L.orc_set_omega(self.h, w)
-    def fill_random(self, seed): self.L.orc_fill_random(self.h, seed)
+    def fill_random(self, seed, amplitude=1.0): self.L.orc_fill_random_scaled(self.h, seed, amplitude)
     def apply_bc(self, which=0): self.L.orc_apply_bc(self.h, which)
     def predict(self): self.L.orc_predict(self.h)
     def source(self): return self.L.orc_source(self.h)

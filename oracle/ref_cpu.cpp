@@ -484,13 +484,14 @@ double* orc_field(void* h, int id) { Arr* a = field(*static_cast<Oracle*>(h), id
 size_t orc_field_count(void* h, int id) { Arr* a = field(*static_cast<Oracle*>(h), id); return a ? a->a.size() : 0; }
 uint8_t* orc_mask(void* h) { return static_cast<Oracle*>(h)->fluid.data(); }
 
-void orc_fill_random(void* h, uint64_t seed) {
+void orc_fill_random_scaled(void* h, uint64_t seed, double amplitude) {
   Oracle& o = *static_cast<Oracle*>(h);
   for (int id = 0; id < PM_FIELD_COUNT; ++id) {
     Arr* a = field(o, id);
-    for (size_t k = 0; k < a->a.size(); ++k) a->a[k] = synth(seed, id, k);
+    for (size_t k = 0; k < a->a.size(); ++k) a->a[k] = amplitude * synth(seed, id, k);
   }
 }
+void orc_fill_random(void* h, uint64_t seed) { orc_fill_random_scaled(h, seed, 1.0); }
 double orc_synth(uint64_t seed, int fieldid, uint64_t flat) { return synth(seed, fieldid, flat); }
 
 void orc_apply_bc(void* h, int which) { apply_bc(*static_cast<Oracle*>(h), which); }

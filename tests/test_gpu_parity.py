@@ -163,23 +163,62 @@ def test_large_grid_jacobi_bit_exact(pm, orc, nx, ny):
     assert_fields_equal(S, O, range(6), "large jacobi")
 
 
-def test_large_grid_properties_8192(pm):
-    """BASELINE configs[3] size, where the oracle is too slow: properties the path must keep.
-    (a) determinism: two runs give identical bits; (b) residuals of successive red-black iterates
-    decrease from the cold start; (c) the correction removes divergence where the reference's
-    Dirichlet-south quirk allows it (max|div| drops by > 10x after K = 40 sweeps)."""
+TILED_CASES = [
+    # case, nx, ny, method, T
+    (0, 48, 48, RB, 1), (0, 48, 48, RB, 2), (0, 250, 131, RB, 2), (0, 250, 131, RB, 3), (0, 117, 61, RB, 3),
+    (1, 93, 31, RB, 1), (1, 93, 31, RB, 2), (1, 300, 70, RB, 2), (1, 300, 70, RB, 3), (1, 121, 77, RB, 3),
+    (0, 48, 48, JAC, 1), (0, 250, 131, JAC, 2), (0, 250, 131, JAC, 4), (1, 93, 31, JAC, 1), (1, 300, 70, JAC, 2), (1, 300, 70, JAC, 4),
+]
+
+
+@pytest.mark.parametrize("case_id,nx,ny,method,T", TILED_CASES)
+@pytest.mark.parametrize("K", [7, 24])
+def test_tiled_ppe_bit_exact(pm, orc, case_id, nx, ny, method, T, K):
+    """The TMA-tiled, temporally blocked pressure solve (T sweeps per pass, K not a multiple of T)
+    against the oracle: iterate, residual and iteration count, 0 ulp."""
+    cfg = make_cfg(pm, case_id, nx, ny, method, 1, K, 0.9 if method == JAC else None, path=2)
+    cfg.sweeps_per_pass = T
+    S, O = pm.Solver(cfg), orc.Oracle(cfg)
+    S.fill_random(17); O.fill_random(17)
+    rs, ro = S.ppe_solve(), O.ppe_solve()
+    assert (rs.iterations, rs.hit_cap) == (ro.iterations, ro.hit_cap)
+    assert rs.residual == ro.residual, (rs.residual, ro.residual)
+    assert_fields_equal(S, O, (2,), "tiled ppe")
+
+
+@pytest.mark.parametrize("case_id,nx,ny,T,steps", [(0, 40, 40, 2, 4), (0, 40, 40, 3, 4), (1, 93, 31, 2, 2), (1, 93, 31, 3, 2)])
+def test_tiled_stopping_rule_bit_exact(pm, orc, case_id, nx, ny, T, steps):
+    """Run to the reference tolerance through the tiled path: the device-side loop test plus the
+    partial replay pass must land on exactly the iterate the oracle stops at."""
+    cfg = make_cfg(pm, case_id, nx, ny, RB, 1, 10000, path=2)
+    cfg.sweeps_per_pass = T
+    S, O = pm.Solver(cfg), orc.Oracle(cfg)
+    S.apply_bc(0); O.apply_bc(0)
+    for n in range(steps):
+        rs, ro = S.step(1), O.step(1)
+        assert (rs.iterations, rs.residual) == (ro.iterations, ro.residual), f"step {n}"
+    assert_fields_equal(S, O, range(6), "tiled whole steps")
+
+
+@pytest.mark.parametrize("exact", [1, 0])
+def test_large_grid_8192_tiled_equals_general_path(pm, exact):
+    """BASELINE configs[3] size, where the oracle is too slow: the tiled path must give the same bits
+    as the general path (itself pinned to the oracle at smaller sizes)."""
     n = 8192
-    cfg = make_cfg(pm, 0, n, n, RB, 0, 40, path=0)
-    S = pm.Solver(cfg)
     out = []
-    for rep in range(2):
-        S.fill_random(5)
+    for path, T in ((1, 0), (2, 2), (2, 3)):
+        cfg = make_cfg(pm, 0, n, n, RB, exact, 9, path=path)
+        cfg.sweeps_per_pass = T
+        S = pm.Solver(cfg)
+        S.fill_random(5, 2.0 ** -10)
         r = S.step(1)
-        assert r.iterations == 40 and r.hit_cap == 1
-        out.append((r.residual, S.download(2)))
-    assert out[0][0] == out[1][0]
-    assert bits_equal(out[0][1], out[1][1])
-    assert np.isfinite(out[0][1]).all()
+        assert r.iterations == 9 and r.hit_cap == 1
+        out.append((r.residual, S.download(2), S.download(0)))
+        S.close()
+    for o in out[1:]:
+        assert o[0] == out[0][0]
+        assert bits_equal(o[1], out[0][1]) and bits_equal(o[2], out[0][2])
+    assert np.isfinite(out[0][1]).all() and np.abs(out[0][1]).max() > 0
 
 
 def test_sor_lex_reports_unsupported_on_multirank(pm):
