@@ -690,7 +690,7 @@ extern "C" int pm_ppe_solve(pm_solver* s, pm_ppe_result* out) {
     CK(cudaMemsetAsync(s->pl[PL_P1], 0, s->plane * sizeof(double), s->stream));
     s->p_cur = PL_P0;
   }
-  if (!cav && c.ppe_method == PM_PPE_JACOBI) {
+  if (!cav && (c.ppe_method == PM_PPE_JACOBI || s->use_tiled)) {  // ping-pong solves: both buffers carry the corner ghosts
     k_copy_corners<<<1, 32, 0, s->stream>>>(k, s->pl[s->p_cur], s->pl[s->p_cur == PL_P0 ? PL_P1 : PL_P0]);
     CKL(s);
   }
