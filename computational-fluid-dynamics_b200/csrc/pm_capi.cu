@@ -445,19 +445,29 @@ extern "C" int pm_fill_random_scaled(pm_solver* s, uint64_t seed, double amplitu
 // ---------------------------------------------------------------------------
 // halo exchange between slabs (no-ops on a single rank)
 // ---------------------------------------------------------------------------
-// One halo row each way: my top interior row -> upper rank's row 0; my bottom interior row -> lower rank's row nyl+1.
-static int exchange_halo1(pm_solver* s, double* plane) {
+// `depth` halo rows each way on `stream`: my top interior rows nyl-depth+1..nyl -> the upper rank's rows
+// 1-depth..0; my bottom interior rows 1..depth -> the lower rank's rows nyl+1..nyl+depth.  Rows are
+// contiguous in the pitched plane, so each direction is one message of depth*pitch doubles.
+static int exchange_halo(pm_solver* s, double* plane, int depth, cudaStream_t stream) {
   if (s->cfg.nranks == 1) return PM_OK;
   const KP& k = s->kp;
+  if (depth > k.padr || depth > k.nyl) return fail(s, PM_ERR_UNSUPPORTED, "halo depth %d exceeds pad rows %d or slab height %d", depth, k.padr, k.nyl);
   std::string e;
-  const size_t n = size_t(k.pitch);
-  double* row_top = plane + size_t(k.padr + k.nyl) * k.pitch;        // send up
-  double* halo_top = plane + size_t(k.padr + k.nyl + 1) * k.pitch;   // recv from up
-  double* row_bot = plane + size_t(k.padr + 1) * k.pitch;            // send down
-  double* halo_bot = plane + size_t(k.padr + 0) * k.pitch;           // recv from down
-  if (!pm_nccl_exchange(&s->nccl, s->stream, k.last_rank ? nullptr : row_top, k.last_rank ? nullptr : halo_top,
-                        k.first_rank ? nullptr : row_bot, k.first_rank ? nullptr : halo_bot, n, &e))
+  const size_t n = size_t(k.pitch) * depth;
+  double* send_up = plane + size_t(k.padr + k.nyl - depth + 1) * k.pitch;
+  double* recv_up = plane + size_t(k.padr + k.nyl + 1) * k.pitch;
+  double* send_dn = plane + size_t(k.padr + 1) * k.pitch;
+  double* recv_dn = plane + size_t(k.padr + 1 - depth) * k.pitch;
+  if (!pm_nccl_exchange(&s->nccl, stream, k.last_rank ? nullptr : send_up, k.last_rank ? nullptr : recv_up,
+                        k.first_rank ? nullptr : send_dn, k.first_rank ? nullptr : recv_dn, n, &e))
     return fail(s, PM_ERR_NCCL, "%s", e.c_str());
+  return PM_OK;
+}
+static int exchange_halo1(pm_solver* s, double* plane) { return exchange_halo(s, plane, 1, s->stream); }
+static int allreduce_res(pm_solver* s, int m_first, int count) {
+  if (s->cfg.nranks == 1 || count <= 0) return PM_OK;
+  std::string e;
+  if (!pm_nccl_allreduce_max_u64(&s->nccl, s->stream, s->d_res + m_first, size_t(count), &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
   return PM_OK;
 }
 
@@ -520,7 +530,21 @@ extern "C" int pm_source(pm_solver* s) {
     s->f_max_valid = true;
     return PM_OK;
   }
-  if (s->cfg.nranks > 1) return fail(s, PM_ERR_UNSUPPORTED, "channel/step source mean over slabs is not implemented yet");
+  if (s->cfg.nranks > 1) {
+    if (exact) return fail(s, PM_ERR_UNSUPPORTED, "exact_arith keeps the reference's serial source sum, which does not shard; use exact_arith=0 with nranks > 1");
+    std::string e;
+    if (!pm_nccl_allreduce_max_u64(&s->nccl, s->stream, &s->d_state->maxf_bits, 1, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
+    k_sum_partials<<<1, 1024, 0, s->stream>>>(s->d_partial, s->n_partial, s->d_state);  // local sum -> ke_sum scratch
+    CKL(s);
+    if (!pm_nccl_allreduce_sum_f64(&s->nccl, s->stream, &s->d_state->ke_sum, 1, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
+    k_mean_from_sum<<<1, 1, 0, s->stream>>>(k.fluid_count_global, s->d_state);
+    CKL(s);
+    k_sub_mean<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+    CKL(s);
+    if (!pm_nccl_allreduce_max_u64(&s->nccl, s->stream, &s->d_state->maxf2_bits, 1, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
+    s->f_max_valid = true;
+    return PM_OK;
+  }
   if (exact) {
     k_mean_serial<<<1, 32, 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
     CKL(s);
@@ -574,6 +598,7 @@ static int launch_iteration_simple(pm_solver* s, int krel, int kabs) {
     PMTRY(exchange_halo1(s, dst));
     k_residual<A, FORM><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, dst, f, s->mask, s->d_state, s->d_res, krel, 0);
     CKL(s);
+    PMTRY(allreduce_res(s, kabs, 1));
   } else {
     double* p = s->pl[s->p_cur];
     k_rb_colour<A, FORM><<<half_grid(k), cell_block(), 0, s->stream>>>(k, p, f, s->mask, s->d_state, s->d_res, krel, 0, 1, fuse);
@@ -590,6 +615,7 @@ static int launch_iteration_simple(pm_solver* s, int krel, int kabs) {
     PMTRY(exchange_halo1(s, p));
     k_residual<A, FORM><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, p, f, s->mask, s->d_state, s->d_res, krel, 0);
     CKL(s);
+    PMTRY(allreduce_res(s, kabs, 1));
   }
   s->timing.ppe_passes++;
   return PM_OK;
@@ -610,11 +636,56 @@ static int read_state(pm_solver* s) {
 
 // Tiled path: pass n reads buffer in0 ^ (n & 1) holding iterate n*T and writes iterate n*T + nsw to the
 // other buffer.  The loop test runs on the device (tiled_stop); the host only polls the sticky flag.
-static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
+//
+// Slabs: the tile rows whose output the neighbours need (within H rows of the slab edge) are launched
+// first; their H halo rows travel by ncclSend/ncclRecv on the comm stream while the interior tile rows
+// run; the residual maxima of the pass are max-allreduced in stream order before the next pass tests them.
+static int tiled_pass(pm_solver* s, int in, int m0, int nsw, int force) {
   const KP& k = s->kp;
+  const TiledPlan& pl = s->tiled;
+  const double* f = s->pl[PL_F];
+  if (s->cfg.nranks == 1) {
+    CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, 0, pl.tiles_y, s->stream));
+    s->timing.kernel_launches++;
+  } else {
+    // edge tile rows: row 0, and as many rows from the top as cover the last H output rows
+    int top = 1;
+    while (top < pl.tiles_y && k.nyl - (pl.tiles_y - top) * pl.ty < pl.halo) ++top;
+    const int bot = 1;
+    if (bot + top >= pl.tiles_y) {
+      CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, 0, pl.tiles_y, s->stream));
+      s->timing.kernel_launches++;
+      if (nsw > 0) PMTRY(exchange_halo(s, pl.p[in ^ 1], pl.halo, s->stream));
+    } else {
+      CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, 0, bot, s->stream));
+      CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, pl.tiles_y - top, top, s->stream));
+      s->timing.kernel_launches += 2;
+      if (nsw > 0) {
+        CK(cudaEventRecord(s->ev_edge, s->stream));
+        CK(cudaStreamWaitEvent(s->comm_stream, s->ev_edge, 0));
+        PMTRY(exchange_halo(s, pl.p[in ^ 1], pl.halo, s->comm_stream));
+        CK(cudaEventRecord(s->ev_halo, s->comm_stream));
+      }
+      CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, bot, pl.tiles_y - bot - top, s->stream));
+      s->timing.kernel_launches++;
+      if (nsw > 0) CK(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+    }
+    // entries m0 .. m0+max(nsw,1)-1 are now complete on this rank (both colour parts)
+    const int lo = std::max(m0, 1), hi = m0 + std::max(nsw, 1) - 1;
+    if (!force) PMTRY(allreduce_res(s, lo, hi - lo + 1));
+  }
+  s->timing.ppe_passes++;
+  return PM_OK;
+}
+
+static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
   const TiledPlan& pl = s->tiled;
   const int K = s->cfg.max_iters, T = pl.sweeps;
   const int in0 = s->p_cur == PL_P0 ? 0 : 1;
+  if (s->cfg.nranks > 1) {  // halos of the inputs: f once per solve, p as deep as one pass reaches
+    PMTRY(exchange_halo(s, s->pl[PL_F], pl.halo, s->stream));
+    PMTRY(exchange_halo(s, pl.p[in0], pl.halo, s->stream));
+  }
   int m = 0, n = 0;
   bool done = false;
   int chunk = s->cfg.poll_chunk > 0 ? s->cfg.poll_chunk : std::max(4, std::min(128, s->last_iters / (8 * T)));
@@ -622,9 +693,7 @@ static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
     int launched = 0;
     while (m < K && launched < chunk) {
       const int nsw = std::min(T, K - m);
-      CK(tiled_launch(&pl, k, in0 ^ (n & 1), s->pl[PL_F], s->d_state, s->d_res, m, nsw, 0, 0, pl.tiles_y, s->stream));
-      s->timing.kernel_launches++;
-      s->timing.ppe_passes++;
+      PMTRY(tiled_pass(s, in0 ^ (n & 1), m, nsw, 0));
       m += nsw; ++n; ++launched;
     }
     PMTRY(read_state(s));
@@ -632,9 +701,7 @@ static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
     if (s->cfg.poll_chunk <= 0) chunk = std::min(128, chunk * 2);
   }
   if (!done) {  // residual of the last iterate (and the loop test for the iterates of the last pass)
-    CK(tiled_launch(&pl, k, in0 ^ (n & 1), s->pl[PL_F], s->d_state, s->d_res, m, 0, 0, 0, pl.tiles_y, s->stream));
-    s->timing.kernel_launches++;
-    s->timing.ppe_passes++;
+    PMTRY(tiled_pass(s, in0 ^ (n & 1), m, 0, 0));
     PMTRY(read_state(s));
     done = s->h_state->done != 0;
   }
@@ -644,9 +711,7 @@ static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
     const int nb = iters / T, mb = nb * T;
     buf = in0 ^ (nb & 1);
     if (iters > mb) {  // land on the exact iterate: replay the first iters-mb sweeps of that pass
-      CK(tiled_launch(&pl, k, buf, s->pl[PL_F], s->d_state, s->d_res, mb, iters - mb, 1, 0, pl.tiles_y, s->stream));
-      s->timing.kernel_launches++;
-      s->timing.ppe_passes++;
+      PMTRY(tiled_pass(s, buf, mb, iters - mb, 1));
       buf ^= 1;
     }
   } else {

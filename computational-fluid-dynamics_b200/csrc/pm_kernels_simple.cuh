@@ -181,6 +181,7 @@ __global__ void k_mean_from_partials(const double* __restrict__ partial, int n, 
   s = block_sum(s, sh);
   if (threadIdx.x == 0) st->mean = count > 0 ? s / double(count) : 0.0;
 }
+__global__ void k_mean_from_sum(int count, PpeState* __restrict__ st) { st->mean = count > 0 ? st->ke_sum / double(count) : 0.0; }
 // k5 (exact policy): the reference's serial row-major sum (channel-01.cpp:622-625), one warp,
 // every lane adding the same 32 shuffled values in index order.
 __global__ void k_mean_serial(const __grid_constant__ KP k, const double* __restrict__ f, const uint8_t* __restrict__ M,
