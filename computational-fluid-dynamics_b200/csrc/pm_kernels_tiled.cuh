@@ -37,7 +37,7 @@ struct TileCfg {
   static constexpr int SH = NSEG * RPT;           // tile height
   static constexpr int TX = SW - 2 * H;           // output block
   static constexpr int TY = SH - 2 * H;
-  static constexpr int SMEM_BYTES = SH * SW * 8;
+  static constexpr int SMEM_BYTES = (SH + 2) * SW * 8;  // tile + one spare row above and below
   static_assert(TX > 0 && TY > 0, "halo too deep for the tile");
   static_assert(H <= PM_PADR, "halo deeper than the pad rows of the planes");
 };
@@ -81,14 +81,30 @@ __device__ __forceinline__ bool tiled_stop(const PpeState* st, const unsigned lo
   return false;
 }
 
-template <class A, int FORM>
+// INT = the whole tile lies strictly inside the domain: every indicator of the cavity form is 1
+// (neighbor_count == 4) and no cell of the channel form touches a wall ghost.
+template <class A, int FORM, bool INT>
 __device__ __forceinline__ double cell_update(const KP& k, int j, int i, double pc, double pe, double pw, double pn, double ps, double f) {
-  if (FORM == 0) return upd_cavity<A>(k, j, i, pc, pe, pw, pn, ps, f);
+  if (FORM == 0) {
+    if (INT) {  // cavity-01.cpp:651-654 with eps_* == 1 (1*x == x exactly)
+      const double s = A::sub(A::add(A::add(pe, pw), A::add(pn, ps)), A::mul(f, k.hh));
+      return A::add(A::mul(pc, k.om1), A::mul(k.wnc[4], s));
+    }
+    return upd_cavity<A>(k, j, i, pc, pe, pw, pn, ps, f);
+  }
   return upd_channel<A>(k, pc, pe, pw, pn, ps, f);
 }
-template <class A, int FORM>
+template <class A, int FORM, bool INT>
 __device__ __forceinline__ double cell_residual(const KP& k, int j, int i, double pc, double pe, double pw, double pn, double ps, double f) {
-  if (FORM == 0) return res_cavity<A>(k, j, i, pc, pe, pw, pn, ps, f, k.idx2);
+  if (FORM == 0) {
+    if (INT) {  // cavity-01.cpp:670-673 with eps_* == 1
+      double s = A::add(A::sub(pe, pc), A::sub(pw, pc));
+      s = A::add(s, A::sub(pn, pc));
+      s = A::add(s, A::sub(ps, pc));
+      return A::sub(A::mul(k.idx2, s), f);
+    }
+    return res_cavity<A>(k, j, i, pc, pe, pw, pn, ps, f, k.idx2);
+  }
   return res_channel<A>(k, pc, pe, pw, pn, ps, f);
 }
 
@@ -98,67 +114,72 @@ struct Cells {
   double p0[RPT], p1[RPT], f0[RPT], f1[RPT];
 };
 
-// One colour half-sweep (red-black) over the thread's rows.  PX: the target of row r is the .x cell
-// iff (r & 1) == PX.  PRE: accumulate the residual of the iterate being replaced (operands before
-// the update) ; POST: of the iterate being created (operands after).  commit=false: residual only.
-template <class A, int FORM, class C, int PX, bool PRE, bool POST>
-__device__ __forceinline__ void rb_half(const KP& k, double* __restrict__ tile, Cells<C::RPT>& c, int rr0, int c0, int i0, int jg0,
-                                        unsigned mW, unsigned mO, bool colW0, bool colW1, bool colO0, bool colO1, bool commit,
-                                        double& rmax_pre, double& rmax_post) {
-  constexpr int SW = C::SW, SH = C::SH, RPT = C::RPT;
+// max over |x| with the semantics of std::max(m, std::abs(x)) (a NaN never replaces m).
+__device__ __forceinline__ void acc_max(double& m, double x, bool on) {
+  const double a = fabs(x);
+  if (on && a > m) m = a;
+}
+
+// One colour half-sweep (red-black) over the thread's rows.  `tp` points at the thread's first cell
+// (row rr0, column c0) of the shared tile, which has one spare row above and below so that the
+// never-used neighbour reads of ring cells stay in bounds: every shared access is tp + constant.
+// PX: the target of row r is the .x cell iff (r & 1) == PX.  PRE: accumulate the residual of the iterate
+// being replaced (operands before the update); POST: of the iterate being created (operands after).
+// mOut: bit 2r / 2r+1 = the .x / .y cell of row r belongs to the output block (residual is taken there).
+//
+// INT tiles update EVERY cell they hold, ring included: a ring cell only ever feeds cells that are already
+// stale for the same half-sweep count (see the header), so the predicate would buy nothing; boundary
+// tiles keep it because ghost cells and cells beyond the domain must keep their values.
+template <class A, int FORM, bool INT, class C, int PX, bool PRE, bool POST>
+__device__ __forceinline__ void rb_half(const KP& k, double* __restrict__ tp, Cells<C::RPT>& c, int i0, int jg0, unsigned mW, unsigned mOut,
+                                        bool colW0, bool colW1, bool commit, double& rmax_pre, double& rmax_post) {
+  constexpr int SW = C::SW, RPT = C::RPT;
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
     const bool tx = (r & 1) == PX;  // compile-time after unrolling
-    const int rr = rr0 + r;
     const int j = jg0 + r;
-    const int col = tx ? c0 : c0 + 1;
     const int i = tx ? i0 : i0 + 1;
+    double* cell = tp + r * SW + (tx ? 0 : 1);
     const double pc = tx ? c.p0[r] : c.p1[r];
     const double fc = tx ? c.f0[r] : c.f1[r];
     double pw, pe, pn, ps;
-    if (tx) {
-      pw = tile[rr * SW + max(col - 1, 0)];
-      pe = c.p1[r];
-    } else {
-      pw = c.p0[r];
-      pe = tile[rr * SW + min(col + 1, SW - 1)];
-    }
+    if (tx) { pw = cell[-1]; pe = c.p1[r]; }
+    else { pw = c.p0[r]; pe = cell[1]; }
     if (r + 1 < RPT) pn = tx ? c.p0[r + 1] : c.p1[r + 1];
-    else pn = tile[min(rr + 1, SH - 1) * SW + col];
+    else pn = cell[SW];
     if (r >= 1) ps = tx ? c.p0[r - 1] : c.p1[r - 1];
-    else ps = tile[max(rr - 1, 0) * SW + col];
-    const bool rowW = (mW >> r) & 1u, rowO = (mO >> r) & 1u;
-    const bool upd = commit && rowW && (tx ? colW0 : colW1);
-    const bool out = rowO && (tx ? colO0 : colO1);
-    if (PRE) {
-      const double rs = cell_residual<A, FORM>(k, j, i, pc, pe, pw, pn, ps, fc);
-      if (out) rmax_pre = fmax(rmax_pre, fabs(rs));
-    }
-    const double nv = cell_update<A, FORM>(k, j, i, pc, pe, pw, pn, ps, fc);
-    if (upd) {
+    else ps = cell[-SW];
+    const bool out = (mOut >> (2 * r + (tx ? 0 : 1))) & 1u;
+    if (PRE) acc_max(rmax_pre, cell_residual<A, FORM, INT>(k, j, i, pc, pe, pw, pn, ps, fc), out);
+    const double nv = cell_update<A, FORM, INT>(k, j, i, pc, pe, pw, pn, ps, fc);
+    if (INT) {
       if (tx) c.p0[r] = nv; else c.p1[r] = nv;
-      tile[rr * SW + col] = nv;
-      if (FORM == 1) {  // refresh the wall ghosts this cell owns (channel-01.cpp:531-541)
-        if (i == 1) { pw = nv; tile[rr * SW + col - 1] = nv; }
-        if (i == k.nx) {
-          pe = 0.0;
-          tile[rr * SW + col + 1] = 0.0;
-          if (tx) c.p1[r] = 0.0;
+      cell[0] = nv;
+      if (POST) acc_max(rmax_post, cell_residual<A, FORM, INT>(k, j, i, nv, pe, pw, pn, ps, fc), out);
+    } else {
+      const bool upd = commit && ((mW >> r) & 1u) && (tx ? colW0 : colW1);
+      if (upd) {
+        if (tx) c.p0[r] = nv; else c.p1[r] = nv;
+        cell[0] = nv;
+        if (FORM == 1) {  // refresh the wall ghosts this cell owns (channel-01.cpp:531-541)
+          if (i == 1) { pw = nv; cell[-1] = nv; }
+          if (i == k.nx) {
+            pe = 0.0;
+            cell[1] = 0.0;
+            if (tx) c.p1[r] = 0.0;
+          }
+          if (j == 1) {
+            ps = nv;
+            cell[-SW] = nv;
+            if (r >= 1) { if (tx) c.p0[r - 1] = nv; else c.p1[r - 1] = nv; }
+          }
+          if (j == k.ny) {
+            pn = nv;
+            cell[SW] = nv;
+            if (r + 1 < RPT) { if (tx) c.p0[r + 1] = nv; else c.p1[r + 1] = nv; }
+          }
         }
-        if (j == 1) {
-          ps = nv;
-          tile[(rr - 1) * SW + col] = nv;
-          if (r >= 1) { if (tx) c.p0[r - 1] = nv; else c.p1[r - 1] = nv; }
-        }
-        if (j == k.ny) {
-          pn = nv;
-          tile[(rr + 1) * SW + col] = nv;
-          if (r + 1 < RPT) { if (tx) c.p0[r + 1] = nv; else c.p1[r + 1] = nv; }
-        }
-      }
-      if (POST) {
-        const double rs = cell_residual<A, FORM>(k, j, i, nv, pe, pw, pn, ps, fc);
-        if (out) rmax_post = fmax(rmax_post, fabs(rs));
+        if (POST) acc_max(rmax_post, cell_residual<A, FORM, INT>(k, j, i, nv, pe, pw, pn, ps, fc), out);
       }
     }
   }
@@ -166,71 +187,110 @@ __device__ __forceinline__ void rb_half(const KP& k, double* __restrict__ tile, 
 
 // One Jacobi sweep: new values of both cells of every row from the previous iterate, staged in
 // registers until every thread has finished reading.
-template <class A, int FORM, class C>
-__device__ __forceinline__ void jacobi_sweep(const KP& k, double* __restrict__ tile, Cells<C::RPT>& c, int rr0, int c0, int i0, int jg0,
-                                             unsigned mW, unsigned mO, bool colW0, bool colW1, bool colO0, bool colO1, bool commit,
-                                             double& rmax_pre) {
-  constexpr int SW = C::SW, SH = C::SH, RPT = C::RPT;
+template <class A, int FORM, bool INT, class C>
+__device__ __forceinline__ void jacobi_sweep(const KP& k, double* __restrict__ tp, Cells<C::RPT>& c, int i0, int jg0, unsigned mW, unsigned mOut,
+                                             bool colW0, bool colW1, bool commit, double& rmax_pre) {
+  constexpr int SW = C::SW, RPT = C::RPT;
   double n0[RPT], n1[RPT];
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
-    const int rr = rr0 + r, j = jg0 + r;
-    const double wl = tile[rr * SW + max(c0 - 1, 0)];
-    const double er = tile[rr * SW + min(c0 + 2, SW - 1)];
+    const int j = jg0 + r;
+    double* cell = tp + r * SW;
+    const double wl = cell[-1];
+    const double er = cell[2];
     double pn0, pn1, ps0, ps1;
     if (r + 1 < RPT) { pn0 = c.p0[r + 1]; pn1 = c.p1[r + 1]; }
-    else { const double2 t = *reinterpret_cast<const double2*>(&tile[min(rr + 1, SH - 1) * SW + c0]); pn0 = t.x; pn1 = t.y; }
+    else { const double2 t = *reinterpret_cast<const double2*>(cell + SW); pn0 = t.x; pn1 = t.y; }
     if (r >= 1) { ps0 = c.p0[r - 1]; ps1 = c.p1[r - 1]; }
-    else { const double2 t = *reinterpret_cast<const double2*>(&tile[max(rr - 1, 0) * SW + c0]); ps0 = t.x; ps1 = t.y; }
-    const bool rowO = (mO >> r) & 1u;
-    const double r0v = cell_residual<A, FORM>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0[r]);
-    const double r1v = cell_residual<A, FORM>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1[r]);
-    if (rowO && colO0) rmax_pre = fmax(rmax_pre, fabs(r0v));
-    if (rowO && colO1) rmax_pre = fmax(rmax_pre, fabs(r1v));
-    n0[r] = cell_update<A, FORM>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0[r]);
-    n1[r] = cell_update<A, FORM>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1[r]);
+    else { const double2 t = *reinterpret_cast<const double2*>(cell - SW); ps0 = t.x; ps1 = t.y; }
+    acc_max(rmax_pre, cell_residual<A, FORM, INT>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0[r]), (mOut >> (2 * r)) & 1u);
+    acc_max(rmax_pre, cell_residual<A, FORM, INT>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1[r]), (mOut >> (2 * r + 1)) & 1u);
+    n0[r] = cell_update<A, FORM, INT>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0[r]);
+    n1[r] = cell_update<A, FORM, INT>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1[r]);
   }
   if (!commit) return;  // uniform across the block
   __syncthreads();      // every neighbour value of the old iterate has been read
+  if (INT) {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      c.p0[r] = n0[r];
+      c.p1[r] = n1[r];
+      *reinterpret_cast<double2*>(tp + r * SW) = make_double2(n0[r], n1[r]);
+    }
+    __syncthreads();
+    return;
+  }
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
-    const int rr = rr0 + r, j = jg0 + r;
+    double* cell = tp + r * SW;
     const bool rowW = (mW >> r) & 1u;
-    if (rowW && colW0) {
-      c.p0[r] = n0[r];
-      tile[rr * SW + c0] = n0[r];
-    }
-    if (rowW && colW1) {
-      c.p1[r] = n1[r];
-      tile[rr * SW + c0 + 1] = n1[r];
-    }
+    if (rowW && colW0) { c.p0[r] = n0[r]; cell[0] = n0[r]; }
+    if (rowW && colW1) { c.p1[r] = n1[r]; cell[1] = n1[r]; }
     if (FORM == 1 && rowW) {  // wall ghosts from the new values
-      if (colW0 && i0 == 1) tile[rr * SW + c0 - 1] = n0[r];
-      if (colW0 && i0 == k.nx) { tile[rr * SW + c0 + 1] = 0.0; c.p1[r] = 0.0; }
-      if (colW1 && i0 + 1 == k.nx) tile[rr * SW + c0 + 2] = 0.0;
+      if (colW0 && i0 == 1) cell[-1] = n0[r];
+      if (colW0 && i0 == k.nx) { cell[1] = 0.0; c.p1[r] = 0.0; }
+      if (colW1 && i0 + 1 == k.nx) cell[2] = 0.0;
     }
   }
   if (FORM == 1) {
     // row ghosts: after all new values are in place (a ghost row register may belong to this thread)
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
-      const int rr = rr0 + r, j = jg0 + r;
+      const int j = jg0 + r;
+      double* cell = tp + r * SW;
       const bool rowW = (mW >> r) & 1u;
       if (!rowW) continue;
       if (j == 1) {
-        if (colW0) { tile[(rr - 1) * SW + c0] = n0[r]; if (r >= 1) c.p0[r - 1] = n0[r]; }
-        if (colW1) { tile[(rr - 1) * SW + c0 + 1] = n1[r]; if (r >= 1) c.p1[r - 1] = n1[r]; }
+        if (colW0) { cell[-SW] = n0[r]; if (r >= 1) c.p0[r - 1] = n0[r]; }
+        if (colW1) { cell[1 - SW] = n1[r]; if (r >= 1) c.p1[r - 1] = n1[r]; }
       }
       if (j == k.ny) {
-        if (colW0) { tile[(rr + 1) * SW + c0] = n0[r]; if (r + 1 < RPT) c.p0[r + 1] = n0[r]; }
-        if (colW1) { tile[(rr + 1) * SW + c0 + 1] = n1[r]; if (r + 1 < RPT) c.p1[r + 1] = n1[r]; }
+        if (colW0) { cell[SW] = n0[r]; if (r + 1 < RPT) c.p0[r + 1] = n0[r]; }
+        if (colW1) { cell[1 + SW] = n1[r]; if (r + 1 < RPT) c.p1[r + 1] = n1[r]; }
       }
     }
   }
   __syncthreads();
 }
 
-template <class A, int FORM, int METHOD, int T>
+// All sweeps of one pass for one thread.  The sweep loop is NOT unrolled (the instruction footprint of
+// the hot path stays within the instruction cache); per-iterate residual maxima therefore go to shared
+// memory at the end of every sweep: warp shuffle tree, then one shared atomicMax per warp.
+// PAR0 = colour of the .x cell of the thread's first row = (j0 & 1): i0 is always odd and TY, RPT are even,
+// so it is the same for every thread of every tile of a launch.
+template <class A, int FORM, int METHOD, int T, bool INT, int PAR0>
+__device__ __forceinline__ void run_sweeps(const KP& k, double* __restrict__ tp, Cells<TileCfg<METHOD, T>::RPT>& c, int i0, int jg0,
+                                           unsigned mW, unsigned mOut, bool colW0, bool colW1, int nsw,
+                                           unsigned long long* __restrict__ red) {
+  using C = TileCfg<METHOD, T>;
+  const int lane = threadIdx.x & 31;
+  double r_cur = 0.0, r_next = 0.0;  // residual maxima of iterate m0+t and m0+t+1
+  const int nloop = nsw > 0 ? nsw : 1;
+#pragma unroll 1
+  for (int t = 0; t < nloop; ++t) {
+    const bool commit = t < nsw;
+    if (METHOD == PM_PPE_SOR_RB) {
+      // colour 0 first ((i + j) even), as the oracle's red-black restatement
+      rb_half<A, FORM, INT, C, PAR0, true, false>(k, tp, c, i0, jg0, mW, mOut, colW0, colW1, commit, r_cur, r_next);
+      if (commit) {
+        __syncthreads();
+        rb_half<A, FORM, INT, C, 1 - PAR0, false, true>(k, tp, c, i0, jg0, mW, mOut, colW0, colW1, true, r_cur, r_next);
+        __syncthreads();
+      }
+    } else {
+      jacobi_sweep<A, FORM, INT, C>(k, tp, c, i0, jg0, mW, mOut, colW0, colW1, commit, r_cur);
+    }
+    const double v = warp_max(r_cur);
+    if (lane == 0 && v > 0.0) atomicMax(&red[t], (unsigned long long)__double_as_longlong(v));
+    r_cur = r_next;
+    r_next = 0.0;
+  }
+  // colour-1 part of the last iterate created (red-black); zero for Jacobi
+  const double v = warp_max(r_cur);
+  if (lane == 0 && v > 0.0) atomicMax(&red[nloop], (unsigned long long)__double_as_longlong(v));
+}
+
+template <class A, int FORM, int METHOD, int T, int PAR0>
 __global__ void __launch_bounds__(PM_TILE_THREADS, 2)
     k_ppe_tiled(const __grid_constant__ KP k, const __grid_constant__ CUtensorMap tmap_in, double* __restrict__ pout,
                 const double* __restrict__ f, PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits, int m0,
@@ -238,9 +298,9 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, 2)
   using C = TileCfg<METHOD, T>;
   constexpr int H = C::H, SW = C::SW, SH = C::SH, RPT = C::RPT, TX = C::TX, TY = C::TY;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  double* tile = reinterpret_cast<double*>(smem_raw);
+  double* tile = reinterpret_cast<double*>(smem_raw) + SW;  // one spare row above (and one below)
   __shared__ __align__(8) uint64_t mbar;
-  __shared__ double red[(T + 1) * 8];
+  __shared__ unsigned long long red[T + 1];  // bit patterns of the residual maxima of iterates m0 .. m0+T
 
   const int tid = threadIdx.x;
   if (!force) {
@@ -261,9 +321,10 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, 2)
     mbar_init(&mbar, 1);
     fence_mbar_init();
   }
+  if (tid <= T) red[tid] = 0ull;
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(&mbar, C::SMEM_BYTES);
+    mbar_expect_tx(&mbar, SH * SW * 8);
     tma_load_2d(tile, &tmap_in, &mbar, PM_OFFC + ib, k.padr + jb);
   }
 
@@ -283,6 +344,9 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, 2)
     if (rowI && rr >= 1 && rr <= SH - 2) mW |= 1u << r;
     if (jl >= 1 && jl <= k.nyl && rr >= H && rr < H + TY) mO |= 1u << r;
   }
+  // Every updatable cell of the tile strictly inside the domain (uniform over the block)?
+  const bool interior = ib + 1 >= 2 && ib + SW - 2 <= k.nx - 1 && k.j0 + jb + 1 >= 2 && k.j0 + jb + SH - 2 <= k.ny - 1 &&
+                        jb + SH - 1 <= k.nyl + H;
 
   // f: HBM -> registers, 128-bit row loads, overlapping the TMA transfer of p
   Cells<RPT> c;
@@ -299,38 +363,24 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, 2)
       c.f1[r] = v.y;
     }
   }
+  double* tp = tile + rr0 * SW + c0;
   mbar_wait(&mbar, 0);
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
-    const double2 v = *reinterpret_cast<const double2*>(&tile[(rr0 + r) * SW + c0]);
+    const double2 v = *reinterpret_cast<const double2*>(tp + r * SW);
     c.p0[r] = v.x;
     c.p1[r] = v.y;
   }
 
-  double rm[T + 1];
+  unsigned mOut = 0;
 #pragma unroll
-  for (int t = 0; t <= T; ++t) rm[t] = 0.0;
-
-  const int par0 = (i0 + jg0) & 1;  // colour of the .x cell of row 0; uniform over the warp
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    if (t < nsw || (t == 0 && nsw == 0)) {
-      const bool commit = t < nsw;
-      if (METHOD == PM_PPE_SOR_RB) {
-        // colour 0 first ((i + j) even), as the oracle's red-black restatement
-        if (par0 == 0) rb_half<A, FORM, C, 0, true, false>(k, tile, c, rr0, c0, i0, jg0, mW, mO, colW0, colW1, colO0, colO1, commit, rm[t], rm[t + 1]);
-        else rb_half<A, FORM, C, 1, true, false>(k, tile, c, rr0, c0, i0, jg0, mW, mO, colW0, colW1, colO0, colO1, commit, rm[t], rm[t + 1]);
-        if (commit) {
-          __syncthreads();
-          if (par0 == 0) rb_half<A, FORM, C, 1, false, true>(k, tile, c, rr0, c0, i0, jg0, mW, mO, colW0, colW1, colO0, colO1, true, rm[t], rm[t + 1]);
-          else rb_half<A, FORM, C, 0, false, true>(k, tile, c, rr0, c0, i0, jg0, mW, mO, colW0, colW1, colO0, colO1, true, rm[t], rm[t + 1]);
-          __syncthreads();
-        }
-      } else {
-        jacobi_sweep<A, FORM, C>(k, tile, c, rr0, c0, i0, jg0, mW, mO, colW0, colW1, colO0, colO1, commit, rm[t]);
-      }
-    }
+  for (int r = 0; r < RPT; ++r) {
+    if (((mO >> r) & 1u) && colO0) mOut |= 1u << (2 * r);
+    if (((mO >> r) & 1u) && colO1) mOut |= 1u << (2 * r + 1);
   }
+  // the residual-only pass (nsw == 0) commits nothing and takes the general code path
+  if (interior && nsw > 0) run_sweeps<A, FORM, METHOD, T, true, PAR0>(k, tp, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red);
+  else run_sweeps<A, FORM, METHOD, T, false, PAR0>(k, tp, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red);
 
   // ---- write the output block: 128-bit stores, plus the wall ghosts its cells own ----
   if (nsw > 0) {
@@ -343,7 +393,7 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, 2)
       if (colO0 && colO1) *reinterpret_cast<double2*>(o) = make_double2(c.p0[r], c.p1[r]);
       else if (colO0) o[0] = c.p0[r];
       else if (colO1) o[1] = c.p1[r];
-      if (FORM == 1) {
+      if (FORM == 1 && !interior) {
         const int j = jg0 + r;
         if (colO0 && i0 == 1) o[-1] = c.p0[r];
         if (colO0 && i0 == k.nx) o[1] = 0.0;
@@ -354,22 +404,14 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, 2)
     }
   }
 
-  // ---- residual norms: warp shuffles, block tree, one atomic per iterate ----
-  const int lane = tid & 31, w = tid >> 5;
-#pragma unroll
-  for (int t = 0; t <= T; ++t) {
-    const double v = warp_max(rm[t]);
-    if (lane == 0) red[t * 8 + w] = v;
-  }
+  // ---- residual norms: one global atomic per iterate and tile ----
   __syncthreads();
   if (tid <= T) {
-    double v = 0.0;
-#pragma unroll
-    for (int q2 = 0; q2 < PM_TILE_THREADS / 32; ++q2) v = fmax(v, red[tid * 8 + q2]);
     const int m = m0 + tid;
-    // Jacobi: rm[t] is the full residual of iterate m0+t (t < max(nsw,1)).  Red-black: rm[t] holds the
-    // red part of iterate m0+t and the black part of the same iterate written by sweep t (rm[t] <- POST of sweep t-1).
-    if (m >= 1 && m <= k.max_iters) atomic_max_nonneg(&res_bits[m], v);
+    // Jacobi: red[t] is the full residual of iterate m0+t.  Red-black: red[t] collects the colour-0 part of
+    // iterate m0+t (before sweep t+1 replaces it) and the colour-1 part taken right after sweep t created it.
+    const unsigned long long v = red[tid];
+    if (v != 0ull && m >= 1 && m <= k.max_iters) atomicMax(&res_bits[m], v);
   }
 }
 
@@ -399,7 +441,9 @@ static inline bool tiled_supported(const pm_config& c, const KP& k) {
 }
 
 template <class A, int FORM, int METHOD, int T>
-static const void* tiled_kernel_ptr() { return reinterpret_cast<const void*>(&k_ppe_tiled<A, FORM, METHOD, T>); }
+static const void* tiled_kernel_ptr(int par0) {
+  return par0 ? reinterpret_cast<const void*>(&k_ppe_tiled<A, FORM, METHOD, T, 1>) : reinterpret_cast<const void*>(&k_ppe_tiled<A, FORM, METHOD, T, 0>);
+}
 
 template <int METHOD, int T>
 static void tiled_geometry(TiledPlan* pl) {
@@ -408,18 +452,18 @@ static void tiled_geometry(TiledPlan* pl) {
 }
 
 template <class A, int FORM>
-static const void* tiled_pick(int method, int T, TiledPlan* pl) {
+static const void* tiled_pick(int method, int T, int par0, TiledPlan* pl) {
   if (method == PM_PPE_SOR_RB) {
     switch (T) {
-      case 1: tiled_geometry<PM_PPE_SOR_RB, 1>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 1>();
-      case 2: tiled_geometry<PM_PPE_SOR_RB, 2>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 2>();
-      case 3: tiled_geometry<PM_PPE_SOR_RB, 3>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 3>();
+      case 1: tiled_geometry<PM_PPE_SOR_RB, 1>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 1>(par0);
+      case 2: tiled_geometry<PM_PPE_SOR_RB, 2>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 2>(par0);
+      case 3: tiled_geometry<PM_PPE_SOR_RB, 3>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 3>(par0);
     }
   } else {
     switch (T) {
-      case 1: tiled_geometry<PM_PPE_JACOBI, 1>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 1>();
-      case 2: tiled_geometry<PM_PPE_JACOBI, 2>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 2>();
-      case 4: tiled_geometry<PM_PPE_JACOBI, 4>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 4>();
+      case 1: tiled_geometry<PM_PPE_JACOBI, 1>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 1>(par0);
+      case 2: tiled_geometry<PM_PPE_JACOBI, 2>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 2>(par0);
+      case 4: tiled_geometry<PM_PPE_JACOBI, 4>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 4>(par0);
     }
   }
   return nullptr;
@@ -429,8 +473,9 @@ static inline bool tiled_create(TiledPlan* pl, const pm_config& c, const KP& k, 
   int T = c.sweeps_per_pass > 0 ? c.sweeps_per_pass : 2;
   const bool cav = c.case_id == PM_CASE_CAVITY;
   const void* kern = nullptr;
-  if (c.exact_arith) kern = cav ? tiled_pick<Exact, 0>(c.ppe_method, T, pl) : tiled_pick<Exact, 1>(c.ppe_method, T, pl);
-  else kern = cav ? tiled_pick<Fast, 0>(c.ppe_method, T, pl) : tiled_pick<Fast, 1>(c.ppe_method, T, pl);
+  const int par0 = k.j0 & 1;
+  if (c.exact_arith) kern = cav ? tiled_pick<Exact, 0>(c.ppe_method, T, par0, pl) : tiled_pick<Exact, 1>(c.ppe_method, T, par0, pl);
+  else kern = cav ? tiled_pick<Fast, 0>(c.ppe_method, T, par0, pl) : tiled_pick<Fast, 1>(c.ppe_method, T, par0, pl);
   if (!kern) { *err = "sweeps_per_pass " + std::to_string(T) + " not built for this method (red-black: 1,2,3; jacobi: 1,2,4)"; return false; }
   pl->kernel = kern;
   pl->tiles_x = (k.nx + pl->tx - 1) / pl->tx;
