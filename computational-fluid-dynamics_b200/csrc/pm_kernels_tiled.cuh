@@ -131,7 +131,7 @@ __device__ __forceinline__ void acc_max(double& m, double x, bool on) {
 // stale for the same half-sweep count (see the header), so the predicate would buy nothing; boundary
 // tiles keep it because ghost cells and cells beyond the domain must keep their values.
 template <class A, int FORM, bool INT, class C, int PX, bool PRE, bool POST>
-__device__ __forceinline__ void rb_half(const KP& k, double* __restrict__ tp, Cells<C::RPT>& c, int i0, int jg0, unsigned mW, unsigned mOut,
+__device__ __forceinline__ void rb_half(const KP& k, double* tp, Cells<C::RPT>& c, int i0, int jg0, unsigned mW, unsigned mOut,
                                         bool colW0, bool colW1, bool commit, double& rmax_pre, double& rmax_post) {
   constexpr int SW = C::SW, RPT = C::RPT;
 #pragma unroll
@@ -188,7 +188,7 @@ __device__ __forceinline__ void rb_half(const KP& k, double* __restrict__ tp, Ce
 // One Jacobi sweep: new values of both cells of every row from the previous iterate, staged in
 // registers until every thread has finished reading.
 template <class A, int FORM, bool INT, class C>
-__device__ __forceinline__ void jacobi_sweep(const KP& k, double* __restrict__ tp, Cells<C::RPT>& c, int i0, int jg0, unsigned mW, unsigned mOut,
+__device__ __forceinline__ void jacobi_sweep(const KP& k, double* tp, Cells<C::RPT>& c, int i0, int jg0, unsigned mW, unsigned mOut,
                                              bool colW0, bool colW1, bool commit, double& rmax_pre) {
   constexpr int SW = C::SW, RPT = C::RPT;
   double n0[RPT], n1[RPT];
@@ -259,7 +259,7 @@ __device__ __forceinline__ void jacobi_sweep(const KP& k, double* __restrict__ t
 // PAR0 = colour of the .x cell of the thread's first row = (j0 & 1): i0 is always odd and TY, RPT are even,
 // so it is the same for every thread of every tile of a launch.
 template <class A, int FORM, int METHOD, int T, bool INT, int PAR0>
-__device__ __forceinline__ void run_sweeps(const KP& k, double* __restrict__ tp, Cells<TileCfg<METHOD, T>::RPT>& c, int i0, int jg0,
+__device__ __forceinline__ void run_sweeps(const KP& k, double* tp, Cells<TileCfg<METHOD, T>::RPT>& c, int i0, int jg0,
                                            unsigned mW, unsigned mOut, bool colW0, bool colW1, int nsw,
                                            unsigned long long* __restrict__ red) {
   using C = TileCfg<METHOD, T>;
