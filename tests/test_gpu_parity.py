@@ -228,3 +228,20 @@ def test_sor_lex_reports_unsupported_on_multirank(pm):
     with pytest.raises(pm.PmError) as e:
         pm.Solver(cfg)
     assert e.value.status == 5
+
+
+def test_multi_gpu_slabs_match_single_gpu():
+    """N > 1 on real GPUs (skipped on a single-GPU box; the CPU/gloo replay of the same schedule is
+    tests/test_slab_gloo.py): torchrun tests/mgpu_check.py, slabs vs single GPU, bit for bit."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "mgpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
