@@ -114,9 +114,10 @@ struct Cells {
   double p0[RPT], p1[RPT], f0[RPT], f1[RPT];
 };
 
-// max over |x| with the semantics of std::max(m, std::abs(x)) (a NaN never replaces m).
+// m = max(m, |x|) where `on`, with the semantics of std::max(m, std::abs(x)) (a NaN never replaces m).
+// |x| is formed by masking the sign bit of the high word (one integer op, no FP64 issue slot).
 __device__ __forceinline__ void acc_max(double& m, double x, bool on) {
-  const double a = fabs(x);
+  const double a = __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x));
   if (on && a > m) m = a;
 }
 
@@ -125,7 +126,7 @@ __device__ __forceinline__ void acc_max(double& m, double x, bool on) {
 // never-used neighbour reads of ring cells stay in bounds: every shared access is tp + constant.
 // PX: the target of row r is the .x cell iff (r & 1) == PX.  PRE: accumulate the residual of the iterate
 // being replaced (operands before the update); POST: of the iterate being created (operands after).
-// mOut: bit 2r / 2r+1 = the .x / .y cell of row r belongs to the output block (residual is taken there).
+// mOut: bit r / bit 16+r = the .x / .y cell of row r belongs to the output block (residual is taken there).
 //
 // INT tiles update EVERY cell they hold, ring included: a ring cell only ever feeds cells that are already
 // stale for the same half-sweep count (see the header), so the predicate would buy nothing; boundary
@@ -134,6 +135,7 @@ template <class A, int FORM, bool INT, class C, int PX, bool PRE, bool POST>
 __device__ __forceinline__ void rb_half(const KP& k, double* tp, Cells<C::RPT>& c, int i0, int jg0, unsigned mW, unsigned mOut,
                                         bool colW0, bool colW1, bool commit, double& rmax_pre, double& rmax_post) {
   constexpr int SW = C::SW, RPT = C::RPT;
+  const unsigned mOx = mOut & 0xffffu, mOy = mOut >> 16;  // output-block rows of the .x / .y column
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
     const bool tx = (r & 1) == PX;  // compile-time after unrolling
@@ -149,7 +151,7 @@ __device__ __forceinline__ void rb_half(const KP& k, double* tp, Cells<C::RPT>& 
     else pn = cell[SW];
     if (r >= 1) ps = tx ? c.p0[r - 1] : c.p1[r - 1];
     else ps = cell[-SW];
-    const bool out = (mOut >> (2 * r + (tx ? 0 : 1))) & 1u;
+    const bool out = ((tx ? mOx : mOy) >> r) & 1u;
     if (PRE) acc_max(rmax_pre, cell_residual<A, FORM, INT>(k, j, i, pc, pe, pw, pn, ps, fc), out);
     const double nv = cell_update<A, FORM, INT>(k, j, i, pc, pe, pw, pn, ps, fc);
     if (INT) {
@@ -203,8 +205,8 @@ __device__ __forceinline__ void jacobi_sweep(const KP& k, double* tp, Cells<C::R
     else { const double2 t = *reinterpret_cast<const double2*>(cell + SW); pn0 = t.x; pn1 = t.y; }
     if (r >= 1) { ps0 = c.p0[r - 1]; ps1 = c.p1[r - 1]; }
     else { const double2 t = *reinterpret_cast<const double2*>(cell - SW); ps0 = t.x; ps1 = t.y; }
-    acc_max(rmax_pre, cell_residual<A, FORM, INT>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0[r]), (mOut >> (2 * r)) & 1u);
-    acc_max(rmax_pre, cell_residual<A, FORM, INT>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1[r]), (mOut >> (2 * r + 1)) & 1u);
+    acc_max(rmax_pre, cell_residual<A, FORM, INT>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0[r]), (mOut >> r) & 1u);
+    acc_max(rmax_pre, cell_residual<A, FORM, INT>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1[r]), (mOut >> (16 + r)) & 1u);
     n0[r] = cell_update<A, FORM, INT>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0[r]);
     n1[r] = cell_update<A, FORM, INT>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1[r]);
   }
@@ -335,15 +337,19 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, 2)
   const bool colI0 = i0 >= 1 && i0 <= k.nx, colI1 = i0 + 1 >= 1 && i0 + 1 <= k.nx;
   const bool colW0 = colI0 && c0 >= 1, colW1 = colI1 && c0 + 1 <= SW - 2;
   const bool colO0 = colI0 && c0 >= H && c0 < H + TX, colO1 = colI1 && c0 + 1 >= H && c0 + 1 < H + TX;
-  unsigned mW = 0, mO = 0, mI = 0;
-#pragma unroll
-  for (int r = 0; r < RPT; ++r) {
-    const int rr = rr0 + r, jl = jl0 + r, j = jg0 + r;
-    const bool rowI = j >= 1 && j <= k.ny && jl >= 1 - H && jl <= k.nyl + H;
-    if (rowI) mI |= 1u << r;
-    if (rowI && rr >= 1 && rr <= SH - 2) mW |= 1u << r;
-    if (jl >= 1 && jl <= k.nyl && rr >= H && rr < H + TY) mO |= 1u << r;
-  }
+  // Row masks as bit ranges over the thread's RPT rows (bit r = row rr0 + r):
+  //   mI: the row holds domain cells this rank has data for;  mW: ... and is not a ring row of the tile;
+  //   mO: the row belongs to the output block and to this rank.
+  auto bit_range = [](int lo, int hi) -> unsigned {  // bits lo..hi of an RPT-bit mask, empty if hi < lo
+    lo = max(lo, 0);
+    hi = min(hi, RPT - 1);
+    return hi >= lo ? ((2u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+  };
+  const int jI_lo = max(1 - k.j0, 1 - H), jI_hi = min(k.ny - k.j0, k.nyl + H);  // jl range with data
+  const unsigned mI = bit_range(jI_lo - jl0, jI_hi - jl0);
+  const unsigned mW = mI & bit_range(1 - rr0, SH - 2 - rr0);
+  const unsigned mO = bit_range(max(1 - jl0, H - rr0), min(k.nyl - jl0, H + TY - 1 - rr0));
+  const unsigned mOut = (colO0 ? mO : 0u) | ((colO1 ? mO : 0u) << 16);
   // Every updatable cell of the tile strictly inside the domain (uniform over the block)?
   const bool interior = ib + 1 >= 2 && ib + SW - 2 <= k.nx - 1 && k.j0 + jb + 1 >= 2 && k.j0 + jb + SH - 2 <= k.ny - 1 &&
                         jb + SH - 1 <= k.nyl + H;
@@ -352,15 +358,24 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, 2)
   Cells<RPT> c;
   {
     const double* fp = f + pm_idx(k, jl0, i0);
+    if (interior) {
 #pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      const bool rowI = (mI >> r) & 1u;
-      double2 v = make_double2(0.0, 0.0);
-      if (rowI && colI0 && colI1) v = __ldg(reinterpret_cast<const double2*>(fp + size_t(r) * k.pitch));
-      else if (rowI && colI0) v.x = __ldg(fp + size_t(r) * k.pitch);
-      else if (rowI && colI1) v.y = __ldg(fp + size_t(r) * k.pitch + 1);
-      c.f0[r] = v.x;
-      c.f1[r] = v.y;
+      for (int r = 0; r < RPT; ++r) {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(fp + size_t(r) * k.pitch));
+        c.f0[r] = v.x;
+        c.f1[r] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        const bool rowI = (mI >> r) & 1u;
+        double2 v = make_double2(0.0, 0.0);
+        if (rowI && colI0 && colI1) v = __ldg(reinterpret_cast<const double2*>(fp + size_t(r) * k.pitch));
+        else if (rowI && colI0) v.x = __ldg(fp + size_t(r) * k.pitch);
+        else if (rowI && colI1) v.y = __ldg(fp + size_t(r) * k.pitch + 1);
+        c.f0[r] = v.x;
+        c.f1[r] = v.y;
+      }
     }
   }
   double* tp = tile + rr0 * SW + c0;
@@ -372,12 +387,6 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, 2)
     c.p1[r] = v.y;
   }
 
-  unsigned mOut = 0;
-#pragma unroll
-  for (int r = 0; r < RPT; ++r) {
-    if (((mO >> r) & 1u) && colO0) mOut |= 1u << (2 * r);
-    if (((mO >> r) & 1u) && colO1) mOut |= 1u << (2 * r + 1);
-  }
   // the residual-only pass (nsw == 0) commits nothing and takes the general code path
   if (interior && nsw > 0) run_sweeps<A, FORM, METHOD, T, true, PAR0>(k, tp, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red);
   else run_sweeps<A, FORM, METHOD, T, false, PAR0>(k, tp, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red);
