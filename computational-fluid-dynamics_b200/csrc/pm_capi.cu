@@ -16,6 +16,7 @@
 #include "pm_common.cuh"
 #include "pm_kernels_simple.cuh"
 #include "pm_kernels_tiled.cuh"
+#include "pm_kernels_lex.cuh"
 #include "pm_nccl.hpp"
 
 // ---------------------------------------------------------------------------
@@ -260,7 +261,7 @@ static int create_impl(pm_solver* s, const pm_config* cfg) {
   const bool tiled_ok = tiled_supported(c, k);
   if (c.kernel_path == PM_PATH_TILED && !tiled_ok)
     return fail(s, PM_ERR_UNSUPPORTED, "tiled path supports unmasked jacobi / sor-rb only");
-  s->use_tiled = tiled_ok && (c.kernel_path == PM_PATH_TILED ||
+  s->use_tiled = tiled_ok && c.ppe_method != PM_PPE_SOR_LEX && (c.kernel_path == PM_PATH_TILED ||
                               (c.kernel_path == PM_PATH_AUTO && size_t(c.nx) * size_t(nyl) >= (size_t(1) << 18)));
   if (s->use_tiled) {
     std::string e;
@@ -730,13 +731,47 @@ static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
   return PM_OK;
 }
 
+// Reference ordering: one persistent CTA runs the whole solve (pm_kernels_lex.cuh).
+static int lex_solve(pm_solver* s, int* iters_out, double* res_out) {
+  const KP& k = s->kp;
+  const size_t bytes = size_t(k.ny + 2) * size_t(k.nx + 2) * sizeof(double);
+  const int use_smem = bytes <= size_t(200) * 1024 ? 1 : 0;
+  const int threads = std::min(1024, ((k.nx + 31) / 32) * 32);
+  const size_t smem = use_smem ? bytes : 0;
+  const void* kern;
+  if (k.case_id == PM_CASE_CAVITY) kern = reinterpret_cast<const void*>(&k_ppe_lex<0, false>);
+  else if (k.has_mask) kern = reinterpret_cast<const void*>(&k_ppe_lex<1, true>);
+  else kern = reinterpret_cast<const void*>(&k_ppe_lex<1, false>);
+  if (use_smem) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  double* pg = s->pl[s->p_cur];
+  const double* f = s->pl[PL_F];
+  const uint8_t* m = s->mask;
+  PpeState* st = s->d_state;
+  unsigned long long* rb = s->d_res;
+  int us = use_smem;
+  void* args[] = {(void*)&k, (void*)&pg, (void*)&f, (void*)&m, (void*)&st, (void*)&rb, (void*)&us};
+  CK(cudaLaunchKernel(kern, dim3(1), dim3(threads), args, smem, s->stream));
+  s->timing.kernel_launches++;
+  s->timing.ppe_passes++;
+  PMTRY(read_state(s));
+  const int iters = s->h_state->iters;
+  if (iters >= 1) {
+    CK(cudaMemcpyAsync(s->h_res, s->d_res + iters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    std::memcpy(res_out, s->h_res, 8);
+  } else {
+    *res_out = s->h_state->res_init;
+  }
+  *iters_out = iters;
+  return PM_OK;
+}
+
 extern "C" int pm_ppe_solve(pm_solver* s, pm_ppe_result* out) {
   if (!s) return PM_ERR_INVALID_ARGUMENT;
   CK(cudaSetDevice(s->device));
   const KP& k = s->kp;
   const pm_config& c = s->cfg;
   const bool cav = k.case_id == PM_CASE_CAVITY;
-  if (c.ppe_method == PM_PPE_SOR_LEX) return fail(s, PM_ERR_UNSUPPORTED, "sor-lex (wavefront) kernel is not built yet");
   if (c.nranks > 1 && s->nccl.comm == nullptr) return fail(s, PM_ERR_NCCL, "communicator missing");
 
   CK(cudaEventRecord(s->ev_a, s->stream));
@@ -765,7 +800,9 @@ extern "C" int pm_ppe_solve(pm_solver* s, pm_ppe_result* out) {
 
   int iters = 0;
   double res = 0.0;
-  if (s->use_tiled) {
+  if (c.ppe_method == PM_PPE_SOR_LEX) {
+    PMTRY(lex_solve(s, &iters, &res));
+  } else if (s->use_tiled) {
     PMTRY(tiled_solve(s, &iters, &res));
   } else {
     if (c.ppe_method != PM_PPE_JACOBI) PMTRY(exchange_halo1(s, s->pl[s->p_cur]));
