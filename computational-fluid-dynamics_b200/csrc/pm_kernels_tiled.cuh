@@ -26,19 +26,29 @@
 
 #include "pm_common.cuh"
 
-#define PM_TILE_THREADS 256
+#ifndef PM_TILE_NSEG
+#define PM_TILE_NSEG 5   // row segments per tile; 64 threads (column pairs) each
+#endif
+#ifndef PM_TILE_RPT
+#define PM_TILE_RPT 8    // rows per thread (even: keeps the colour of a thread's first row uniform over the launch)
+#endif
+#ifndef PM_TILE_MINBLOCKS
+#define PM_TILE_MINBLOCKS 2
+#endif
+#define PM_TILE_THREADS (64 * PM_TILE_NSEG)
 
 template <int METHOD, int T>
 struct TileCfg {
   static constexpr int H = (METHOD == PM_PPE_SOR_RB) ? 2 * T : ((T + 1) / 2) * 2;  // even: keeps 16-byte alignment of row pairs
   static constexpr int SW = 128;                  // tile width in doubles == 64 column pairs == one TMA box row (1 KiB)
   static constexpr int NSEG = PM_TILE_THREADS / 64;
-  static constexpr int RPT = 10;                  // rows per thread
+  static constexpr int RPT = PM_TILE_RPT;         // rows per thread
   static constexpr int SH = NSEG * RPT;           // tile height
   static constexpr int TX = SW - 2 * H;           // output block
   static constexpr int TY = SH - 2 * H;
   static constexpr int SMEM_BYTES = (SH + 2) * SW * 8;  // tile + one spare row above and below
   static_assert(TX > 0 && TY > 0, "halo too deep for the tile");
+  static_assert(RPT % 2 == 0 && TY % 2 == 0, "PAR0 (colour of a thread's first row) must not depend on the segment or the tile row");
   static_assert(H <= PM_PADR, "halo deeper than the pad rows of the planes");
 };
 
@@ -293,7 +303,7 @@ __device__ __forceinline__ void run_sweeps(const KP& k, double* tp, Cells<TileCf
 }
 
 template <class A, int FORM, int METHOD, int T, int PAR0>
-__global__ void __launch_bounds__(PM_TILE_THREADS, 2)
+__global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
     k_ppe_tiled(const __grid_constant__ KP k, const __grid_constant__ CUtensorMap tmap_in, double* __restrict__ pout,
                 const double* __restrict__ f, PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits, int m0,
                 int nsw, int force, int tile_row0) {
@@ -305,6 +315,20 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, 2)
   __shared__ unsigned long long red[T + 1];  // bit patterns of the residual maxima of iterates m0 .. m0+T
 
   const int tid = threadIdx.x;
+  const int bx = blockIdx.x, by = blockIdx.y + tile_row0;
+  const int x0 = 1 + bx * TX, y0 = 1 + by * TY;  // first output cell (i, jl)
+  const int ib = x0 - H, jb = y0 - H;            // tile origin (i, jl)
+
+  // The tile load goes out before anything else; the loop test of the reference (which needs three
+  // dependent global loads) is evaluated while the TMA is in flight.
+  if (tid == 0) {
+    mbar_init(&mbar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(&mbar, SH * SW * 8);
+    tma_load_2d(tile, &tmap_in, &mbar, PM_OFFC + ib, k.padr + jb);
+  }
+  if (tid <= T) red[tid] = 0ull;
+  __syncthreads();
   if (!force) {
     int first = -1;
     if (tiled_stop(st, res_bits, m0, T, &first)) {
@@ -312,22 +336,9 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, 2)
         st->iters = first;
         st->done = 1;
       }
+      mbar_wait(&mbar, 0);  // never leave with a bulk copy still landing in this CTA's shared memory
       return;
     }
-  }
-  const int bx = blockIdx.x, by = blockIdx.y + tile_row0;
-  const int x0 = 1 + bx * TX, y0 = 1 + by * TY;  // first output cell (i, jl)
-  const int ib = x0 - H, jb = y0 - H;            // tile origin (i, jl)
-
-  if (tid == 0) {
-    mbar_init(&mbar, 1);
-    fence_mbar_init();
-  }
-  if (tid <= T) red[tid] = 0ull;
-  __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&mbar, SH * SW * 8);
-    tma_load_2d(tile, &tmap_in, &mbar, PM_OFFC + ib, k.padr + jb);
   }
 
   const int q = tid & 63, sg = tid >> 6;
@@ -479,7 +490,7 @@ static const void* tiled_pick(int method, int T, int par0, TiledPlan* pl) {
 }
 
 static inline bool tiled_create(TiledPlan* pl, const pm_config& c, const KP& k, double* p0, double* p1, int rows_alloc, std::string* err) {
-  int T = c.sweeps_per_pass > 0 ? c.sweeps_per_pass : 2;
+  int T = c.sweeps_per_pass > 0 ? c.sweeps_per_pass : (c.ppe_method == PM_PPE_SOR_RB ? 3 : 2);
   const bool cav = c.case_id == PM_CASE_CAVITY;
   const void* kern = nullptr;
   const int par0 = k.j0 & 1;

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libpm.so")
+LIB_PATH = os.environ.get("PM_LIB") or os.path.join(HERE, "lib", "libpm.so")  # PM_LIB: experimental builds (make variant)
 
 PM_OK = 0
 CASE_CAVITY, CASE_CHANNEL, CASE_STEP = 0, 1, 2
