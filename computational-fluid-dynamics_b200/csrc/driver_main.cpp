@@ -7,13 +7,17 @@
 // 733-769; backwards_step-01.cpp:551-607,1018-1061).  All numerics run on the GPU through include/pm.h; the
 // host only formats text.  Flags beyond the README's are extras and default to the reference behaviour.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <filesystem>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pm.h"
@@ -56,6 +60,7 @@ struct Options {
   bool vtk = true;
   std::string outdir = "vtk_output";
   int device = -1;
+  int gpus = 1;  // j-slabs, one host thread + one handle per GPU of this box (NCCL between them)
 };
 
 [[noreturn]] void usage(const char* prog) {
@@ -63,7 +68,7 @@ struct Options {
                "usage: %s [--Re R] [--Nx N] [--Ny N] [--dt T]\n"
                "          [--steps N | --tfinal T] [--ppe sor-rb|jacobi|sor-lex] [--max-iters K] [--exact 0|1]\n"
                "          [--path auto|simple|tiled] [--sweeps T] [--print-interval N] [--save-interval N]\n"
-               "          [--no-vtk] [--outdir DIR] [--device D]\n"
+               "          [--no-vtk] [--outdir DIR] [--device D] [--gpus N]\n"
                "Omitted flags keep the reference's compiled-in constants.\n",
                prog);
   std::exit(2);
@@ -89,6 +94,7 @@ Options parse(int argc, char** argv) {
     else if (f == "--print-interval") o.print_interval = std::atoi(val());
     else if (f == "--save-interval") o.save_interval = std::atoi(val());
     else if (f == "--device") o.device = std::atoi(val());
+    else if (f == "--gpus") o.gpus = std::atoi(val());
     else if (f == "--outdir") o.outdir = val();
     else if (f == "--no-vtk") o.vtk = false;
     else if (f == "--ppe") {
@@ -128,15 +134,8 @@ struct Snapshot {
 };
 
 // interpolateToCellCenters (cavity-01.cpp:717-733; backwards_step-01.cpp:981-1009: solid cells stay 0)
-void fetch(pm_solver* s, const pm_config& c, Snapshot& sn) {
+void centres(const pm_config& c, Snapshot& sn) {
   const int nx = c.nx, ny = c.ny;
-  sn.nx = nx; sn.ny = ny;
-  sn.u.resize(size_t(ny + 2) * (nx + 1));
-  sn.v.resize(size_t(ny + 1) * (nx + 2));
-  sn.p.resize(size_t(ny + 2) * (nx + 2));
-  check(pm_download(s, PM_FIELD_U, sn.u.data(), sn.u.size()), s, "download u");
-  check(pm_download(s, PM_FIELD_V, sn.v.data(), sn.v.size()), s, "download v");
-  check(pm_download(s, PM_FIELD_P, sn.p.data(), sn.p.size()), s, "download p");
   sn.uc.assign(size_t(ny + 2) * (nx + 2), 0.0);
   sn.vc.assign(size_t(ny + 2) * (nx + 2), 0.0);
   for (int j = 1; j <= ny; ++j)
@@ -230,28 +229,64 @@ void write_pvd(const std::string& path, const std::vector<std::string>& files, c
   if (std::fclose(f) != 0) throw std::runtime_error("Error writing collection file: " + path);
 }
 
+// Reusable barrier for the per-GPU host threads (C++17 has no std::barrier).
+class Barrier {
+ public:
+  explicit Barrier(int n) : n_(n) {}
+  void wait() {
+    std::unique_lock<std::mutex> lk(m_);
+    const int gen = gen_;
+    if (++count_ == n_) { count_ = 0; ++gen_; cv_.notify_all(); }
+    else cv_.wait(lk, [&] { return gen != gen_; });
+  }
+ private:
+  std::mutex m_;
+  std::condition_variable cv_;
+  int n_, count_ = 0, gen_ = 0;
+};
+
 struct Run {
   pm_config cfg{};
   pm_solver* s = nullptr;
   Options opt;
+  int rank = 0, nranks = 1;
+  Barrier* bar = nullptr;      // null on a single GPU
+  Snapshot* shared = nullptr;  // rank 0's snapshot; every rank downloads its own rows into it
   Snapshot snap;
   std::vector<std::string> files;
   std::vector<double> times;
   int total_steps = 0, print_interval = 100, save_interval = 100;
 
+  void sync_ranks() { if (bar) bar->wait(); }
+
   void export_frame(int step, double t) {
     if (!opt.vtk) return;
+    Snapshot& sn = shared ? *shared : snap;
     try {
       char name[256];
       std::snprintf(name, sizeof name, "%s_%06d.vtk", kText[cfg.case_id].vtk_base, step);
-      fetch(s, cfg, snap);
-      write_vtk(opt.outdir + "/" + name, cfg, snap, t);
-      files.emplace_back(name);
-      times.push_back(t);
-      if (step % print_interval == 0 || step == 0) std::printf("%sExported VTK file: %s%s\n", BLUE, name, RESET);
+      if (rank == 0) {  // size the host arrays once; pm_download then fills only the caller's rows
+        sn.nx = cfg.nx; sn.ny = cfg.ny;
+        sn.u.resize(size_t(cfg.ny + 2) * (cfg.nx + 1));
+        sn.v.resize(size_t(cfg.ny + 1) * (cfg.nx + 2));
+        sn.p.resize(size_t(cfg.ny + 2) * (cfg.nx + 2));
+      }
+      sync_ranks();
+      check(pm_download(s, PM_FIELD_U, sn.u.data(), sn.u.size()), s, "download u");
+      check(pm_download(s, PM_FIELD_V, sn.v.data(), sn.v.size()), s, "download v");
+      check(pm_download(s, PM_FIELD_P, sn.p.data(), sn.p.size()), s, "download p");
+      sync_ranks();
+      if (rank == 0) {
+        centres(cfg, sn);
+        write_vtk(opt.outdir + "/" + name, cfg, sn, t);
+        files.emplace_back(name);
+        times.push_back(t);
+        if (step % print_interval == 0 || step == 0) std::printf("%sExported VTK file: %s%s\n", BLUE, name, RESET);
+      }
     } catch (const std::exception& e) {  // an export failure is logged, the run goes on (cavity-01.cpp:479-481)
       std::fprintf(stderr, "%sError exporting VTK data: %s%s\n", RED, e.what(), RESET);
     }
+    sync_ranks();
   }
 
   void banner() const {
@@ -274,7 +309,8 @@ struct Run {
 
   void log_line(int step, double t, const pm_ppe_result& r) {
     double md = 0.0, ke = 0.0;
-    check(pm_diagnostics(s, &md, &ke), s, "diagnostics");
+    check(pm_diagnostics(s, &md, &ke), s, "diagnostics");  // collective over the slabs
+    if (rank != 0) return;
     if (cfg.case_id == PM_CASE_CAVITY)
       std::printf("Step %6d/%d | t=%6.2f | max(div)=%10.2e | avg_KE=%10.6f | SOR_iters=%4d\n", step, total_steps, t, md, ke, r.iterations);
     else
@@ -284,9 +320,14 @@ struct Run {
 
   int main_loop() {
     const int cs = cfg.case_id;
-    if (cs == PM_CASE_STEP) {  // setupGeometry's report, printed before the stream turns fixed (backwards_step-01.cpp:495-531)
-      std::vector<uint8_t> m(size_t(cfg.ny + 2) * (cfg.nx + 2));
-      check(pm_download_mask(s, m.data(), m.size()), s, "mask");
+    const bool root = rank == 0;
+    Snapshot& sn0 = shared ? *shared : snap;
+    if (root) sn0.fluid.assign(size_t(cfg.ny + 2) * (cfg.nx + 2), 0);
+    sync_ranks();
+    check(pm_download_mask(s, sn0.fluid.data(), sn0.fluid.size()), s, "mask");  // each rank fills its rows
+    sync_ranks();
+    if (root && cs == PM_CASE_STEP) {  // setupGeometry's report, printed before the stream turns fixed (backwards_step-01.cpp:495-531)
+      const std::vector<uint8_t>& m = sn0.fluid;
       int fluid = 0;
       for (int j = 1; j <= cfg.ny; ++j)
         for (int i = 1; i <= cfg.nx; ++i) fluid += m[size_t(j) * (cfg.nx + 2) + i];
@@ -294,7 +335,7 @@ struct Run {
                   CYAN, 2.0, cfg.step_i_location, 1.0, cfg.inlet_j_max, cfg.ly, cfg.ny, RESET);
       std::printf("%sGeometry setup complete. Fluid cells: %d/%d%s\n", BLUE, fluid, cfg.nx * cfg.ny, RESET);
     }
-    if (opt.vtk) {
+    if (root && opt.vtk) {
       try {
         std::filesystem::create_directories(opt.outdir);
       } catch (const std::filesystem::filesystem_error& e) {
@@ -302,20 +343,18 @@ struct Run {
       }
       std::printf("%sCreated output directory: %s%s\n", BLUE, opt.outdir.c_str(), RESET);
     }
-    banner();
-    snap.fluid.resize(size_t(cfg.ny + 2) * (cfg.nx + 2));
-    check(pm_download_mask(s, snap.fluid.data(), snap.fluid.size()), s, "mask");
+    if (root) banner();
     // frame 0: the channel/step constructors and the cavity's run() apply the BCs and export before stepping
-    if (cs == PM_CASE_CAVITY) std::printf("%s%s%s", GREEN, kText[cs].start_msg, RESET);
+    if (root && cs == PM_CASE_CAVITY) std::printf("%s%s%s", GREEN, kText[cs].start_msg, RESET);
     check(pm_apply_bc(s, 0), s, "apply_bc");
     export_frame(0, 0.0);
-    if (cs != PM_CASE_CAVITY) std::printf("%s%s%s", GREEN, kText[cs].start_msg, RESET);
+    if (root && cs != PM_CASE_CAVITY) std::printf("%s%s%s", GREEN, kText[cs].start_msg, RESET);
 
     for (int step = 1; step <= total_steps; ++step) {
       const double t = step * cfg.dt;
       pm_ppe_result r{};
       check(pm_step(s, 1, &r), s, "step");
-      if (r.hit_cap) {
+      if (root && r.hit_cap) {
         if (cs == PM_CASE_CAVITY)
           std::fprintf(stderr, "Warning: SOR solver did not converge in %d iterations. Final residual: %g\n", cfg.max_iters, r.residual);
         else
@@ -324,7 +363,7 @@ struct Run {
       if (step % print_interval == 0 || step == total_steps) log_line(step, t, r);
       if (step % save_interval == 0 || step == total_steps) export_frame(step, t);
     }
-    if (opt.vtk) {
+    if (root && opt.vtk) {
       try {
         const std::string pvd = std::string(kText[cs].vtk_base) + "_animation.pvd";
         write_pvd(opt.outdir + "/" + pvd, files, times);
@@ -333,7 +372,7 @@ struct Run {
         std::fprintf(stderr, "%sError creating ParaView collection: %s%s\n", RED, e.what(), RESET);
       }
     }
-    std::printf("%sSimulation completed successfully!\nVTK files saved in directory: %s\nOpen '%s/%s_animation.pvd' in ParaView for animation\n%s", GREEN,
+    if (root) std::printf("%sSimulation completed successfully!\nVTK files saved in directory: %s\nOpen '%s/%s_animation.pvd' in ParaView for animation\n%s", GREEN,
                 opt.outdir.c_str(), opt.outdir.c_str(), kText[cs].vtk_base, RESET);
     return 0;
   }
@@ -359,11 +398,38 @@ int main(int argc, char** argv) {
     run.total_steps = o.steps >= 0 ? o.steps : c.total_steps;
     run.print_interval = o.print_interval > 0 ? o.print_interval : c.print_interval;
     run.save_interval = o.save_interval > 0 ? o.save_interval : c.save_interval;
-    const int st = pm_create(&c, &run.s);
-    if (st != PM_OK) throw std::runtime_error(pm_last_error(nullptr));
-    const int rc = run.main_loop();
-    pm_destroy(run.s);
-    return rc;
+    if (o.gpus <= 1) {
+      const int st = pm_create(&c, &run.s);
+      if (st != PM_OK) throw std::runtime_error(pm_last_error(nullptr));
+      const int rc = run.main_loop();
+      pm_destroy(run.s);
+      return rc;
+    }
+    // One host thread and one handle per GPU; the handles talk NCCL among themselves inside pm_step.
+    if (c.ppe_method == PM_PPE_SOR_LEX) throw std::runtime_error("sor-lex does not shard over GPUs; use sor-rb or jacobi with --gpus");
+    if (pm_nccl_unique_id(c.nccl_id) != PM_OK) throw std::runtime_error(pm_last_error(nullptr));
+    Barrier bar(o.gpus);
+    std::vector<Run> runs(o.gpus, run);
+    std::vector<std::string> errors(o.gpus);
+    std::vector<std::thread> th;
+    for (int r = 0; r < o.gpus; ++r) {
+      Run& me = runs[r];
+      me.rank = r; me.nranks = o.gpus; me.bar = &bar; me.shared = &runs[0].snap;
+      me.cfg.rank = r; me.cfg.nranks = o.gpus; me.cfg.device = r;
+      th.emplace_back([&me, &errors, r] {
+        try {
+          if (pm_create(&me.cfg, &me.s) != PM_OK) throw std::runtime_error(pm_last_error(nullptr));
+          me.main_loop();
+        } catch (const std::exception& e) {
+          errors[r] = e.what();
+          std::fprintf(stderr, "Error (rank %d): %s\n", r, e.what());
+          std::_Exit(1);  // the other ranks are blocked in a collective; there is nothing to unwind to
+        }
+        if (me.s) pm_destroy(me.s);
+      });
+    }
+    for (auto& t : th) t.join();
+    return 0;
   } catch (const std::exception& e) {
     if (colour_err) std::fprintf(stderr, "%sError: %s%s\n", RED, e.what(), RESET);
     else std::fprintf(stderr, "Error: %s\n", e.what());
