@@ -210,8 +210,13 @@ def run_ours(args):
     ms_per_pass = ppe_ms / passes if passes else float("nan")
     achieved = bytes_per_pass / (ms_per_pass * 1e-3) / 1e9
     step_bytes = bytes_per_cell_step(K_ITERS) * nx * ny_local
+    traffic = None  # measured DRAM bytes per launch (ncu), when this exact workload was profiled
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and world == 1 and args.ppe == "rb" and not args.exact:
+        key = f"k_ppe_tiled<Fast,0,1,{int(round(sweeps_per_pass + 0.4))},0> {nx}x{ny}"
+        traffic = json.load(open(tpath)).get(key, {}).get("dram_bytes_per_launch")
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "kernel": "pressure sweep pass (sweep(s) + fused inf-norm residual)", "peak_source": peak_src,
         "algorithmic_bytes_per_launch": bytes_per_pass, "ms_per_launch": ms_per_pass, "sweeps_per_launch": sweeps_per_pass,
         "whole_step": {"algorithmic_GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,
