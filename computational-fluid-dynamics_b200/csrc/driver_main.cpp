@@ -60,6 +60,7 @@ struct Options {
   bool vtk = true;
   std::string outdir = "vtk_output";
   int device = -1;
+  int stop_after = 0;  // leave the time loop after this many steps (banner and "Step n/N" still show the full run)
   int gpus = 1;  // j-slabs, one host thread + one handle per GPU of this box (NCCL between them)
 };
 
@@ -68,7 +69,7 @@ struct Options {
                "usage: %s [--Re R] [--Nx N] [--Ny N] [--dt T]\n"
                "          [--steps N | --tfinal T] [--ppe sor-rb|jacobi|sor-lex] [--max-iters K] [--exact 0|1]\n"
                "          [--path auto|simple|tiled] [--sweeps T] [--print-interval N] [--save-interval N]\n"
-               "          [--no-vtk] [--outdir DIR] [--device D] [--gpus N]\n"
+               "          [--no-vtk] [--outdir DIR] [--device D] [--gpus N] [--stop-after N]\n"
                "Omitted flags keep the reference's compiled-in constants.\n",
                prog);
   std::exit(2);
@@ -95,6 +96,7 @@ Options parse(int argc, char** argv) {
     else if (f == "--save-interval") o.save_interval = std::atoi(val());
     else if (f == "--device") o.device = std::atoi(val());
     else if (f == "--gpus") o.gpus = std::atoi(val());
+    else if (f == "--stop-after") o.stop_after = std::atoi(val());
     else if (f == "--outdir") o.outdir = val();
     else if (f == "--no-vtk") o.vtk = false;
     else if (f == "--ppe") {
@@ -362,6 +364,7 @@ struct Run {
       }
       if (step % print_interval == 0 || step == total_steps) log_line(step, t, r);
       if (step % save_interval == 0 || step == total_steps) export_frame(step, t);
+      if (opt.stop_after > 0 && step >= opt.stop_after) break;
     }
     if (root && opt.vtk) {
       try {

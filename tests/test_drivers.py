@@ -1,0 +1,69 @@
+"""GPU tests of the drop-in drivers (bin/cavity, bin/channel): run with the reference's ordering and exact
+arithmetic they must write the SAME BYTES as the unmodified reference programs — stdout (ANSI stripped),
+stderr warnings, and every VTK frame (md5) — recorded in tests/golden/drivers.json by
+tests/golden/make_vtk_golden.py from the reference's own run.  The production ordering (red-black) is checked
+on the printed diagnostics, which agree to the printed precision."""
+import hashlib
+import json
+import os
+import re
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "computational-fluid-dynamics_b200", "bin")
+ANSI = re.compile(r"\x1b\[[0-9;]*m")
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "drivers.json")))
+
+
+def run(exe, args, cwd):
+    p = subprocess.run([os.path.join(BIN, exe)] + args, cwd=cwd, capture_output=True, text=True, timeout=600)
+    return p.returncode, ANSI.sub("", p.stdout).splitlines(), ANSI.sub("", p.stderr).splitlines()
+
+
+def md5(path):
+    return hashlib.md5(open(path, "rb").read()).hexdigest()
+
+
+@pytest.mark.parametrize("exe,case,stop", [("cavity", "cavity", 200), ("channel", "channel", 200)])
+def test_reference_ordering_writes_identical_bytes(tmp_path, exe, case, stop):
+    rc, out, err = run(exe, ["--ppe", "sor-lex", "--exact", "1", "--stop-after", str(stop)], tmp_path)
+    assert rc == 0, err
+    gold = GOLD[case]
+    # stdout up to and including the export of frame `stop` is the reference's, line for line
+    last = f"Exported VTK file: {case}_flow_{stop:06d}.vtk"
+    n = gold["stdout"].index(last) + 1
+    assert out[:n] == gold["stdout"][:n]
+    for step in range(0, stop + 1, 100):
+        name = f"{case}_flow_{step:06d}.vtk"
+        assert md5(tmp_path / "vtk_output" / name) == gold["md5"][name], name
+    if case == "channel":  # step 2 of the reference run stops at the 10000-iteration cap and says so on stderr
+        assert err[:1] == gold["stderr_first"][:1]
+    else:
+        assert err == []
+
+
+def test_readme_flags_and_error_exit(tmp_path):
+    rc, out, err = run("cavity", ["--Re", "100", "--Nx", "128", "--Ny", "128", "--dt", "1e-3", "--stop-after", "2", "--no-vtk"], tmp_path)
+    assert rc == 0
+    assert "Grid: 128x128 (spacing=0.007812)" in out and "Time: dt=0.001000, steps=20000, final_time=20.000000" in out
+    rc, out, err = run("channel", ["--Re", "1000", "--Nx", "256", "--Ny", "64", "--dt", "5e-4", "--stop-after", "1", "--no-vtk"], tmp_path)
+    assert rc == 0 and "Grid: 256x64 (dx=0.011719, dy=0.015625)" in out
+    rc, out, err = run("cavity", ["--dt", "-1"], tmp_path)   # dt <= 0 keeps the CFL rule (flag semantics), so this runs
+    rc, out, err = run("backwards_step", ["--Nx", "8", "--Ny", "8", "--stop-after", "1", "--no-vtk"], tmp_path)
+    assert rc == 1 and err[-1].startswith("Error: Step location is outside computational domain!")
+
+
+def test_production_ordering_prints_the_reference_diagnostics(tmp_path):
+    """Red-black SOR (default) needs more sweeps than the lexicographic order, but max(div) and avg_KE agree
+    with the reference's log to every printed digit over the first 300 steps of the default cavity run."""
+    rc, out, err = run("cavity", ["--stop-after", "300", "--no-vtk"], tmp_path)
+    assert rc == 0
+    ours = [l for l in out if l.startswith("Step")]
+    ref = [l for l in GOLD["cavity"]["stdout"] if l.startswith("Step")][:3]
+    assert len(ours) == 3
+    for a, b in zip(ours, ref):
+        assert a.split("| SOR_iters")[0] == b.split("| SOR_iters")[0]
