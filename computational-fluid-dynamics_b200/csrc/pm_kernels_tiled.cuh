@@ -131,9 +131,15 @@ __device__ __forceinline__ void acc_max(double& m, double x, bool on) {
   if (on && a > m) m = a;
 }
 
-// One colour half-sweep (red-black) over the thread's rows.  `tp` points at the thread's first cell
-// (row rr0, column c0) of the shared tile, which has one spare row above and below so that the
-// never-used neighbour reads of ring cells stay in bounds: every shared access is tp + constant.
+// Shared-memory layout of the exchange tile ("split rows"): within each 128-double row the 64 even columns
+// come first, then the 64 odd ones: column c lives at (c & 1) * 64 + (c >> 1).  Lane q of a warp owns columns
+// 2q (.x) and 2q+1 (.y); its west neighbour 2q-1 and east neighbour 2q+2 then sit at consecutive doubles
+// across the lanes, so every 64-bit access of a sweep is bank-conflict free (the natural layout, stride
+// 16 B across lanes, costs two wavefronts where one suffices).  `tpx` / `tpy` point at the thread's .x / .y cell
+// of its first row.  The tile has one spare row above and below, so the never-used neighbour reads of ring
+// cells stay in bounds and every shared access is tpx/tpy + constant.
+//
+// One colour half-sweep (red-black) over the thread's rows.
 // PX: the target of row r is the .x cell iff (r & 1) == PX.  PRE: accumulate the residual of the iterate
 // being replaced (operands before the update); POST: of the iterate being created (operands after).
 // mOut: bit r / bit 16+r = the .x / .y cell of row r belongs to the output block (residual is taken there).
@@ -142,7 +148,7 @@ __device__ __forceinline__ void acc_max(double& m, double x, bool on) {
 // stale for the same half-sweep count (see the header), so the predicate would buy nothing; boundary
 // tiles keep it because ghost cells and cells beyond the domain must keep their values.
 template <class A, int FORM, bool INT, class C, int PX, bool PRE, bool POST>
-__device__ __forceinline__ void rb_half(const KP& k, double* tp, Cells<C::RPT>& c, int i0, int jg0, unsigned mW, unsigned mOut,
+__device__ __forceinline__ void rb_half(const KP& k, double* tpx, double* tpy, Cells<C::RPT>& c, int i0, int jg0, unsigned mW, unsigned mOut,
                                         bool colW0, bool colW1, bool commit, double& rmax_pre, double& rmax_post) {
   constexpr int SW = C::SW, RPT = C::RPT;
   const unsigned mOx = mOut & 0xffffu, mOy = mOut >> 16;  // output-block rows of the .x / .y column
@@ -151,12 +157,13 @@ __device__ __forceinline__ void rb_half(const KP& k, double* tp, Cells<C::RPT>& 
     const bool tx = (r & 1) == PX;  // compile-time after unrolling
     const int j = jg0 + r;
     const int i = tx ? i0 : i0 + 1;
-    double* cell = tp + r * SW + (tx ? 0 : 1);
+    double* cell = (tx ? tpx : tpy) + r * SW;     // the target
+    double* side = (tx ? tpy - 1 : tpx + 1) + r * SW;  // its outer horizontal neighbour: column 2q-1 resp. 2q+2
     const double pc = tx ? c.p0[r] : c.p1[r];
     const double fc = tx ? c.f0[r] : c.f1[r];
     double pw, pe, pn, ps;
-    if (tx) { pw = cell[-1]; pe = c.p1[r]; }
-    else { pw = c.p0[r]; pe = cell[1]; }
+    if (tx) { pw = side[0]; pe = c.p1[r]; }
+    else { pw = c.p0[r]; pe = side[0]; }
     if (r + 1 < RPT) pn = tx ? c.p0[r + 1] : c.p1[r + 1];
     else pn = cell[SW];
     if (r >= 1) ps = tx ? c.p0[r - 1] : c.p1[r - 1];
@@ -174,11 +181,11 @@ __device__ __forceinline__ void rb_half(const KP& k, double* tp, Cells<C::RPT>& 
         if (tx) c.p0[r] = nv; else c.p1[r] = nv;
         cell[0] = nv;
         if (FORM == 1) {  // refresh the wall ghosts this cell owns (channel-01.cpp:531-541)
-          if (i == 1) { pw = nv; cell[-1] = nv; }
+          if (i == 1) { pw = nv; side[0] = nv; }  // i == 1 is always a .x cell: its west ghost is the outer neighbour
           if (i == k.nx) {
             pe = 0.0;
-            cell[1] = 0.0;
-            if (tx) c.p1[r] = 0.0;
+            if (tx) { c.p1[r] = 0.0; tpy[r * SW] = 0.0; }  // the east ghost is the .y cell of this pair
+            else side[0] = 0.0;
           }
           if (j == 1) {
             ps = nv;
@@ -200,21 +207,20 @@ __device__ __forceinline__ void rb_half(const KP& k, double* tp, Cells<C::RPT>& 
 // One Jacobi sweep: new values of both cells of every row from the previous iterate, staged in
 // registers until every thread has finished reading.
 template <class A, int FORM, bool INT, class C>
-__device__ __forceinline__ void jacobi_sweep(const KP& k, double* tp, Cells<C::RPT>& c, int i0, int jg0, unsigned mW, unsigned mOut,
+__device__ __forceinline__ void jacobi_sweep(const KP& k, double* tpx, double* tpy, Cells<C::RPT>& c, int i0, int jg0, unsigned mW, unsigned mOut,
                                              bool colW0, bool colW1, bool commit, double& rmax_pre) {
   constexpr int SW = C::SW, RPT = C::RPT;
   double n0[RPT], n1[RPT];
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
     const int j = jg0 + r;
-    double* cell = tp + r * SW;
-    const double wl = cell[-1];
-    const double er = cell[2];
+    const double wl = tpy[r * SW - 1];
+    const double er = tpx[r * SW + 1];
     double pn0, pn1, ps0, ps1;
     if (r + 1 < RPT) { pn0 = c.p0[r + 1]; pn1 = c.p1[r + 1]; }
-    else { const double2 t = *reinterpret_cast<const double2*>(cell + SW); pn0 = t.x; pn1 = t.y; }
+    else { pn0 = tpx[(r + 1) * SW]; pn1 = tpy[(r + 1) * SW]; }
     if (r >= 1) { ps0 = c.p0[r - 1]; ps1 = c.p1[r - 1]; }
-    else { const double2 t = *reinterpret_cast<const double2*>(cell - SW); ps0 = t.x; ps1 = t.y; }
+    else { ps0 = tpx[(r - 1) * SW]; ps1 = tpy[(r - 1) * SW]; }
     acc_max(rmax_pre, cell_residual<A, FORM, INT>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0[r]), (mOut >> r) & 1u);
     acc_max(rmax_pre, cell_residual<A, FORM, INT>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1[r]), (mOut >> (16 + r)) & 1u);
     n0[r] = cell_update<A, FORM, INT>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0[r]);
@@ -227,21 +233,21 @@ __device__ __forceinline__ void jacobi_sweep(const KP& k, double* tp, Cells<C::R
     for (int r = 0; r < RPT; ++r) {
       c.p0[r] = n0[r];
       c.p1[r] = n1[r];
-      *reinterpret_cast<double2*>(tp + r * SW) = make_double2(n0[r], n1[r]);
+      tpx[r * SW] = n0[r];
+      tpy[r * SW] = n1[r];
     }
     __syncthreads();
     return;
   }
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
-    double* cell = tp + r * SW;
     const bool rowW = (mW >> r) & 1u;
-    if (rowW && colW0) { c.p0[r] = n0[r]; cell[0] = n0[r]; }
-    if (rowW && colW1) { c.p1[r] = n1[r]; cell[1] = n1[r]; }
+    if (rowW && colW0) { c.p0[r] = n0[r]; tpx[r * SW] = n0[r]; }
+    if (rowW && colW1) { c.p1[r] = n1[r]; tpy[r * SW] = n1[r]; }
     if (FORM == 1 && rowW) {  // wall ghosts from the new values
-      if (colW0 && i0 == 1) cell[-1] = n0[r];
-      if (colW0 && i0 == k.nx) { cell[1] = 0.0; c.p1[r] = 0.0; }
-      if (colW1 && i0 + 1 == k.nx) cell[2] = 0.0;
+      if (colW0 && i0 == 1) tpy[r * SW - 1] = n0[r];
+      if (colW0 && i0 == k.nx) { tpy[r * SW] = 0.0; c.p1[r] = 0.0; }
+      if (colW1 && i0 + 1 == k.nx) tpx[r * SW + 1] = 0.0;
     }
   }
   if (FORM == 1) {
@@ -249,16 +255,15 @@ __device__ __forceinline__ void jacobi_sweep(const KP& k, double* tp, Cells<C::R
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
       const int j = jg0 + r;
-      double* cell = tp + r * SW;
       const bool rowW = (mW >> r) & 1u;
       if (!rowW) continue;
       if (j == 1) {
-        if (colW0) { cell[-SW] = n0[r]; if (r >= 1) c.p0[r - 1] = n0[r]; }
-        if (colW1) { cell[1 - SW] = n1[r]; if (r >= 1) c.p1[r - 1] = n1[r]; }
+        if (colW0) { tpx[(r - 1) * SW] = n0[r]; if (r >= 1) c.p0[r - 1] = n0[r]; }
+        if (colW1) { tpy[(r - 1) * SW] = n1[r]; if (r >= 1) c.p1[r - 1] = n1[r]; }
       }
       if (j == k.ny) {
-        if (colW0) { cell[SW] = n0[r]; if (r + 1 < RPT) c.p0[r + 1] = n0[r]; }
-        if (colW1) { cell[1 + SW] = n1[r]; if (r + 1 < RPT) c.p1[r + 1] = n1[r]; }
+        if (colW0) { tpx[(r + 1) * SW] = n0[r]; if (r + 1 < RPT) c.p0[r + 1] = n0[r]; }
+        if (colW1) { tpy[(r + 1) * SW] = n1[r]; if (r + 1 < RPT) c.p1[r + 1] = n1[r]; }
       }
     }
   }
@@ -271,7 +276,7 @@ __device__ __forceinline__ void jacobi_sweep(const KP& k, double* tp, Cells<C::R
 // PAR0 = colour of the .x cell of the thread's first row = (j0 & 1): i0 is always odd and TY, RPT are even,
 // so it is the same for every thread of every tile of a launch.
 template <class A, int FORM, int METHOD, int T, bool INT, int PAR0>
-__device__ __forceinline__ void run_sweeps(const KP& k, double* tp, Cells<TileCfg<METHOD, T>::RPT>& c, int i0, int jg0,
+__device__ __forceinline__ void run_sweeps(const KP& k, double* tpx, double* tpy, Cells<TileCfg<METHOD, T>::RPT>& c, int i0, int jg0,
                                            unsigned mW, unsigned mOut, bool colW0, bool colW1, int nsw,
                                            unsigned long long* __restrict__ red) {
   using C = TileCfg<METHOD, T>;
@@ -283,14 +288,14 @@ __device__ __forceinline__ void run_sweeps(const KP& k, double* tp, Cells<TileCf
     const bool commit = t < nsw;
     if (METHOD == PM_PPE_SOR_RB) {
       // colour 0 first ((i + j) even), as the oracle's red-black restatement
-      rb_half<A, FORM, INT, C, PAR0, true, false>(k, tp, c, i0, jg0, mW, mOut, colW0, colW1, commit, r_cur, r_next);
+      rb_half<A, FORM, INT, C, PAR0, true, false>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, commit, r_cur, r_next);
       if (commit) {
         __syncthreads();
-        rb_half<A, FORM, INT, C, 1 - PAR0, false, true>(k, tp, c, i0, jg0, mW, mOut, colW0, colW1, true, r_cur, r_next);
+        rb_half<A, FORM, INT, C, 1 - PAR0, false, true>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, true, r_cur, r_next);
         __syncthreads();
       }
     } else {
-      jacobi_sweep<A, FORM, INT, C>(k, tp, c, i0, jg0, mW, mOut, colW0, colW1, commit, r_cur);
+      jacobi_sweep<A, FORM, INT, C>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, commit, r_cur);
     }
     const double v = warp_max(r_cur);
     if (lane == 0 && v > 0.0) atomicMax(&red[t], (unsigned long long)__double_as_longlong(v));
@@ -389,18 +394,29 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
       }
     }
   }
-  double* tp = tile + rr0 * SW + c0;
   mbar_wait(&mbar, 0);
+  {  // TMA delivered natural row order: take the own cells, then rewrite the tile in the split-row layout
+    const double* tn = tile + rr0 * SW + c0;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const double2 v = *reinterpret_cast<const double2*>(tn + r * SW);
+      c.p0[r] = v.x;
+      c.p1[r] = v.y;
+    }
+  }
+  double* tpx = tile + rr0 * SW + q;
+  double* tpy = tpx + SW / 2;
+  __syncthreads();  // every thread holds its cells
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
-    const double2 v = *reinterpret_cast<const double2*>(tp + r * SW);
-    c.p0[r] = v.x;
-    c.p1[r] = v.y;
+    tpx[r * SW] = c.p0[r];
+    tpy[r * SW] = c.p1[r];
   }
+  __syncthreads();
 
   // the residual-only pass (nsw == 0) commits nothing and takes the general code path
-  if (interior && nsw > 0) run_sweeps<A, FORM, METHOD, T, true, PAR0>(k, tp, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red);
-  else run_sweeps<A, FORM, METHOD, T, false, PAR0>(k, tp, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red);
+  if (interior && nsw > 0) run_sweeps<A, FORM, METHOD, T, true, PAR0>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red);
+  else run_sweeps<A, FORM, METHOD, T, false, PAR0>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red);
 
   // ---- write the output block: 128-bit stores, plus the wall ghosts its cells own ----
   if (nsw > 0) {

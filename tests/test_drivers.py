@@ -52,8 +52,8 @@ def test_readme_flags_and_error_exit(tmp_path):
     assert "Grid: 128x128 (spacing=0.007812)" in out and "Time: dt=0.001000, steps=20000, final_time=20.000000" in out
     rc, out, err = run("channel", ["--Re", "1000", "--Nx", "256", "--Ny", "64", "--dt", "5e-4", "--stop-after", "1", "--no-vtk"], tmp_path)
     assert rc == 0 and "Grid: 256x64 (dx=0.011719, dy=0.015625)" in out
-    rc, out, err = run("cavity", ["--dt", "-1"], tmp_path)   # dt <= 0 keeps the CFL rule (flag semantics), so this runs
-    rc, out, err = run("backwards_step", ["--Nx", "8", "--Ny", "8", "--stop-after", "1", "--no-vtk"], tmp_path)
+    # STEP_LOCATION / dx = nx / 4 truncates to 0 for nx = 2: the reference's constructor check fires
+    rc, out, err = run("backwards_step", ["--Nx", "2", "--Ny", "8", "--stop-after", "1", "--no-vtk"], tmp_path)
     assert rc == 1 and err[-1].startswith("Error: Step location is outside computational domain!")
 
 
