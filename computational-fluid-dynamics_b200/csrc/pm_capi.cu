@@ -154,6 +154,7 @@ static void fill_kp(pm_solver* s, int j0, int nyl) {
   k.wnc[0] = 0.0;
   k.denom = 2.0 * (k.idx2 + k.idy2);
   k.rdenom = 1.0 / k.denom;
+  k.cw = c.case_id == PM_CASE_CAVITY ? c.omega * k.hh / 4.0 : c.omega / k.denom;
   if (c.case_id == PM_CASE_CAVITY) {
     const double dti = 1.0 / c.dt;
     k.src_coef = dti * c.rho;               // time_step_inv * density, cavity-01.cpp:624

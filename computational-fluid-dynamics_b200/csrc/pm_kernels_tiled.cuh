@@ -35,6 +35,9 @@
 #ifndef PM_TILE_MINBLOCKS
 #define PM_TILE_MINBLOCKS 2
 #endif
+#ifndef PM_TILE_F_SMEM
+#define PM_TILE_F_SMEM 0  // 1: f lives in shared memory (thread-private, conflict-free layout) instead of registers
+#endif
 #define PM_TILE_THREADS (64 * PM_TILE_NSEG)
 
 template <int METHOD, int T>
@@ -46,7 +49,8 @@ struct TileCfg {
   static constexpr int SH = NSEG * RPT;           // tile height
   static constexpr int TX = SW - 2 * H;           // output block
   static constexpr int TY = SH - 2 * H;
-  static constexpr int SMEM_BYTES = (SH + 2) * SW * 8;  // tile + one spare row above and below
+  static constexpr int F_BYTES = PM_TILE_F_SMEM ? 2 * RPT * PM_TILE_THREADS * 8 : 0;
+  static constexpr int SMEM_BYTES = (SH + 2) * SW * 8 + F_BYTES;  // tile + one spare row above and below (+ f)
   static_assert(TX > 0 && TY > 0, "halo too deep for the tile");
   static_assert(RPT % 2 == 0 && TY % 2 == 0, "PAR0 (colour of a thread's first row) must not depend on the segment or the tile row");
   static_assert(H <= PM_PADR, "halo deeper than the pad rows of the planes");
@@ -121,7 +125,16 @@ __device__ __forceinline__ double cell_residual(const KP& k, int j, int i, doubl
 // Per-thread view of the tile.
 template <int RPT>
 struct Cells {
-  double p0[RPT], p1[RPT], f0[RPT], f1[RPT];
+  double p0[RPT], p1[RPT];
+#if PM_TILE_F_SMEM
+  const double* fs;  // this thread's slot of the f block: value (r, xy) at fs[(2 * r + xy) * PM_TILE_THREADS]
+  __device__ __forceinline__ double f0v(int r) const { return fs[(2 * r) * PM_TILE_THREADS]; }
+  __device__ __forceinline__ double f1v(int r) const { return fs[(2 * r + 1) * PM_TILE_THREADS]; }
+#else
+  double f0[RPT], f1[RPT];
+  __device__ __forceinline__ double f0v(int r) const { return f0[r]; }
+  __device__ __forceinline__ double f1v(int r) const { return f1[r]; }
+#endif
 };
 
 // m = max(m, |x|) where `on`, with the semantics of std::max(m, std::abs(x)) (a NaN never replaces m).
@@ -152,6 +165,7 @@ __device__ __forceinline__ void rb_half(const KP& k, double* tpx, double* tpy, C
                                         bool colW0, bool colW1, bool commit, double& rmax_pre, double& rmax_post) {
   constexpr int SW = C::SW, RPT = C::RPT;
   const unsigned mOx = mOut & 0xffffu, mOy = mOut >> 16;  // output-block rows of the .x / .y column
+  double post_raw = 0.0;  // max |r| before the update over this half-sweep's cells (production interior tiles)
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
     const bool tx = (r & 1) == PX;  // compile-time after unrolling
@@ -160,7 +174,7 @@ __device__ __forceinline__ void rb_half(const KP& k, double* tpx, double* tpy, C
     double* cell = (tx ? tpx : tpy) + r * SW;     // the target
     double* side = (tx ? tpy - 1 : tpx + 1) + r * SW;  // its outer horizontal neighbour: column 2q-1 resp. 2q+2
     const double pc = tx ? c.p0[r] : c.p1[r];
-    const double fc = tx ? c.f0[r] : c.f1[r];
+    const double fc = tx ? c.f0v(r) : c.f1v(r);
     double pw, pe, pn, ps;
     if (tx) { pw = side[0]; pe = c.p1[r]; }
     else { pw = c.p0[r]; pe = side[0]; }
@@ -169,6 +183,19 @@ __device__ __forceinline__ void rb_half(const KP& k, double* tpx, double* tpy, C
     if (r >= 1) ps = tx ? c.p0[r - 1] : c.p1[r - 1];
     else ps = cell[-SW];
     const bool out = ((tx ? mOx : mOy) >> r) & 1u;
+    if (INT && !A::exact) {
+      // Production arithmetic, interior tile: the relaxation in residual form.  With all indicators 1,
+      //   p*(1-w) + (w/4)*(S - f*h*h) == p + (w*h*h/4) * r,   r = h^-2 * sum(p_nb - p) - f   (the reference's residual),
+      // so one FMA on the residual replaces the update tree; and because a colour-1 cell's neighbours do not
+      // change during its half-sweep, its residual after the update is exactly (1-w) * r.  9 FP64 ops per cell
+      // instead of 14; the iterates differ from the reference tree by rounding only (exact_arith=1 keeps the tree).
+      const double rs = cell_residual<A, FORM, true>(k, j, i, pc, pe, pw, pn, ps, fc);
+      const double nvf = fma(k.cw, rs, pc);
+      if (tx) c.p0[r] = nvf; else c.p1[r] = nvf;
+      cell[0] = nvf;
+      acc_max(PRE ? rmax_pre : post_raw, rs, out);
+      continue;
+    }
     if (PRE) acc_max(rmax_pre, cell_residual<A, FORM, INT>(k, j, i, pc, pe, pw, pn, ps, fc), out);
     const double nv = cell_update<A, FORM, INT>(k, j, i, pc, pe, pw, pn, ps, fc);
     if (INT) {
@@ -202,6 +229,10 @@ __device__ __forceinline__ void rb_half(const KP& k, double* tpx, double* tpy, C
       }
     }
   }
+  if (INT && !A::exact && POST) {
+    const double m = fabs(k.om1) * post_raw;  // residual of the iterate just created: (1 - omega) * r
+    if (m > rmax_post) rmax_post = m;
+  }
 }
 
 // One Jacobi sweep: new values of both cells of every row from the previous iterate, staged in
@@ -221,10 +252,17 @@ __device__ __forceinline__ void jacobi_sweep(const KP& k, double* tpx, double* t
     else { pn0 = tpx[(r + 1) * SW]; pn1 = tpy[(r + 1) * SW]; }
     if (r >= 1) { ps0 = c.p0[r - 1]; ps1 = c.p1[r - 1]; }
     else { ps0 = tpx[(r - 1) * SW]; ps1 = tpy[(r - 1) * SW]; }
-    acc_max(rmax_pre, cell_residual<A, FORM, INT>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0[r]), (mOut >> r) & 1u);
-    acc_max(rmax_pre, cell_residual<A, FORM, INT>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1[r]), (mOut >> (16 + r)) & 1u);
-    n0[r] = cell_update<A, FORM, INT>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0[r]);
-    n1[r] = cell_update<A, FORM, INT>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1[r]);
+    const double r0v = cell_residual<A, FORM, INT>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0v(r));
+    const double r1v = cell_residual<A, FORM, INT>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1v(r));
+    acc_max(rmax_pre, r0v, (mOut >> r) & 1u);
+    acc_max(rmax_pre, r1v, (mOut >> (16 + r)) & 1u);
+    if (INT && !A::exact) {  // residual form of the relaxation, see rb_half
+      n0[r] = fma(k.cw, r0v, c.p0[r]);
+      n1[r] = fma(k.cw, r1v, c.p1[r]);
+    } else {
+      n0[r] = cell_update<A, FORM, INT>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0v(r));
+      n1[r] = cell_update<A, FORM, INT>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1v(r));
+    }
   }
   if (!commit) return;  // uniform across the block
   __syncthreads();      // every neighbour value of the old iterate has been read
@@ -370,16 +408,22 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
   const bool interior = ib + 1 >= 2 && ib + SW - 2 <= k.nx - 1 && k.j0 + jb + 1 >= 2 && k.j0 + jb + SH - 2 <= k.ny - 1 &&
                         jb + SH - 1 <= k.nyl + H;
 
-  // f: HBM -> registers, 128-bit row loads, overlapping the TMA transfer of p
+  // f: HBM -> registers (or the thread's private shared-memory slots), 128-bit row loads, overlapping the TMA transfer of p
   Cells<RPT> c;
+#if PM_TILE_F_SMEM
+  double* fsw = reinterpret_cast<double*>(smem_raw) + (SH + 2) * SW + tid;
+  c.fs = fsw;
+#define PM_PUT_F(r, vx, vy) do { fsw[(2 * (r)) * PM_TILE_THREADS] = (vx); fsw[(2 * (r) + 1) * PM_TILE_THREADS] = (vy); } while (0)
+#else
+#define PM_PUT_F(r, vx, vy) do { c.f0[r] = (vx); c.f1[r] = (vy); } while (0)
+#endif
   {
     const double* fp = f + pm_idx(k, jl0, i0);
     if (interior) {
 #pragma unroll
       for (int r = 0; r < RPT; ++r) {
         const double2 v = __ldg(reinterpret_cast<const double2*>(fp + size_t(r) * k.pitch));
-        c.f0[r] = v.x;
-        c.f1[r] = v.y;
+        PM_PUT_F(r, v.x, v.y);
       }
     } else {
 #pragma unroll
@@ -389,11 +433,11 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
         if (rowI && colI0 && colI1) v = __ldg(reinterpret_cast<const double2*>(fp + size_t(r) * k.pitch));
         else if (rowI && colI0) v.x = __ldg(fp + size_t(r) * k.pitch);
         else if (rowI && colI1) v.y = __ldg(fp + size_t(r) * k.pitch + 1);
-        c.f0[r] = v.x;
-        c.f1[r] = v.y;
+        PM_PUT_F(r, v.x, v.y);
       }
     }
   }
+#undef PM_PUT_F
   mbar_wait(&mbar, 0);
   {  // TMA delivered natural row order: take the own cells, then rewrite the tile in the split-row layout
     const double* tn = tile + rr0 * SW + c0;
