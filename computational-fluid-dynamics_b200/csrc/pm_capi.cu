@@ -45,6 +45,7 @@ struct pm_solver {
   bool f_max_valid = false;
   int last_iters = 0;
   bool use_tiled = false;
+  bool use_small = false;  // persistent single-CTA solve (small grids)
   int sweeps = 1;
   TiledPlan tiled{};
   PmNccl nccl{};
@@ -264,6 +265,14 @@ static int create_impl(pm_solver* s, const pm_config* cfg) {
     return fail(s, PM_ERR_UNSUPPORTED, "tiled path supports unmasked jacobi / sor-rb only");
   s->use_tiled = tiled_ok && c.ppe_method != PM_PPE_SOR_LEX && (c.kernel_path == PM_PATH_TILED ||
                               (c.kernel_path == PM_PATH_AUTO && size_t(c.nx) * size_t(nyl) >= (size_t(1) << 18)));
+  {
+    const size_t bytes = size_t(c.ny + 2) * size_t(c.nx + 2) * sizeof(double);
+    const bool small_ok = c.nranks == 1 && c.ppe_method != PM_PPE_SOR_LEX && bytes <= size_t(200) * 1024 &&
+                          size_t(c.nx) * size_t(c.ny) <= size_t(20) * 1024;
+    if (c.kernel_path == PM_PATH_PERSISTENT && !small_ok)
+      return fail(s, PM_ERR_UNSUPPORTED, "persistent path needs a single rank and a pressure field that fits shared memory");
+    s->use_small = small_ok && !s->use_tiled && (c.kernel_path == PM_PATH_PERSISTENT || c.kernel_path == PM_PATH_AUTO);
+  }
   if (s->use_tiled) {
     std::string e;
     if (!tiled_create(&s->tiled, c, k, s->pl[PL_P0], s->pl[PL_P1], s->rows_alloc, &e))
@@ -767,6 +776,45 @@ static int lex_solve(pm_solver* s, int* iters_out, double* res_out) {
   return PM_OK;
 }
 
+template <class A>
+static const void* small_kernel(const KP& k, int method) {
+  const bool rb = method == PM_PPE_SOR_RB;
+  if (k.case_id == PM_CASE_CAVITY)
+    return rb ? reinterpret_cast<const void*>(&k_ppe_small<A, 0, false, PM_PPE_SOR_RB>) : reinterpret_cast<const void*>(&k_ppe_small<A, 0, false, PM_PPE_JACOBI>);
+  if (k.has_mask)
+    return rb ? reinterpret_cast<const void*>(&k_ppe_small<A, 1, true, PM_PPE_SOR_RB>) : reinterpret_cast<const void*>(&k_ppe_small<A, 1, true, PM_PPE_JACOBI>);
+  return rb ? reinterpret_cast<const void*>(&k_ppe_small<A, 1, false, PM_PPE_SOR_RB>) : reinterpret_cast<const void*>(&k_ppe_small<A, 1, false, PM_PPE_JACOBI>);
+}
+// Small grids: Jacobi / red-black in one persistent CTA (pm_kernels_lex.cuh, k_ppe_small).
+static int small_solve(pm_solver* s, int* iters_out, double* res_out) {
+  const KP& k = s->kp;
+  const size_t smem = size_t(k.ny + 2) * size_t(k.nx + 2) * sizeof(double);
+  const int cells = k.nx * k.ny;
+  const int threads = std::min(1024, std::max(128, ((cells / 4 + 31) / 32) * 32));
+  const void* kern = s->cfg.exact_arith ? small_kernel<Exact>(k, s->cfg.ppe_method) : small_kernel<Fast>(k, s->cfg.ppe_method);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  double* pg = s->pl[s->p_cur];
+  const double* f = s->pl[PL_F];
+  const uint8_t* m = s->mask;
+  PpeState* st = s->d_state;
+  unsigned long long* rb = s->d_res;
+  void* args[] = {(void*)&k, (void*)&pg, (void*)&f, (void*)&m, (void*)&st, (void*)&rb};
+  CK(cudaLaunchKernel(kern, dim3(1), dim3(threads), args, smem, s->stream));
+  s->timing.kernel_launches++;
+  s->timing.ppe_passes++;
+  PMTRY(read_state(s));
+  const int iters = s->h_state->iters;
+  if (iters >= 1) {
+    CK(cudaMemcpyAsync(s->h_res, s->d_res + iters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    std::memcpy(res_out, s->h_res, 8);
+  } else {
+    *res_out = s->h_state->res_init;
+  }
+  *iters_out = iters;
+  return PM_OK;
+}
+
 extern "C" int pm_ppe_solve(pm_solver* s, pm_ppe_result* out) {
   if (!s) return PM_ERR_INVALID_ARGUMENT;
   CK(cudaSetDevice(s->device));
@@ -791,7 +839,7 @@ extern "C" int pm_ppe_solve(pm_solver* s, pm_ppe_result* out) {
     CK(cudaMemsetAsync(s->pl[PL_P1], 0, s->plane * sizeof(double), s->stream));
     s->p_cur = PL_P0;
   }
-  if (!cav && (c.ppe_method == PM_PPE_JACOBI || s->use_tiled)) {  // ping-pong solves: both buffers carry the corner ghosts
+  if (!cav && !s->use_small && (c.ppe_method == PM_PPE_JACOBI || s->use_tiled)) {  // ping-pong solves: both buffers carry the corner ghosts
     k_copy_corners<<<1, 32, 0, s->stream>>>(k, s->pl[s->p_cur], s->pl[s->p_cur == PL_P0 ? PL_P1 : PL_P0]);
     CKL(s);
   }
@@ -805,6 +853,8 @@ extern "C" int pm_ppe_solve(pm_solver* s, pm_ppe_result* out) {
     PMTRY(lex_solve(s, &iters, &res));
   } else if (s->use_tiled) {
     PMTRY(tiled_solve(s, &iters, &res));
+  } else if (s->use_small) {
+    PMTRY(small_solve(s, &iters, &res));
   } else {
     if (c.ppe_method != PM_PPE_JACOBI) PMTRY(exchange_halo1(s, s->pl[s->p_cur]));
     const int K = c.max_iters;

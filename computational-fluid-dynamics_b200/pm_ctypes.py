@@ -15,7 +15,7 @@ PM_OK = 0
 CASE_CAVITY, CASE_CHANNEL, CASE_STEP = 0, 1, 2
 PPE_JACOBI, PPE_SOR_RB, PPE_SOR_LEX = 0, 1, 2
 F_U, F_V, F_P, F_USTAR, F_VSTAR, F_F = range(6)
-PATH_AUTO, PATH_SIMPLE, PATH_TILED = 0, 1, 2
+PATH_AUTO, PATH_SIMPLE, PATH_TILED, PATH_PERSISTENT = 0, 1, 2, 3
 
 
 class PmConfig(C.Structure):

@@ -71,7 +71,8 @@ typedef enum pm_field {
 typedef enum pm_kernel_path {
   PM_PATH_AUTO = 0,
   PM_PATH_SIMPLE = 1, /* one global-memory pass per colour + separate residual pass */
-  PM_PATH_TILED = 2   /* TMA-staged shared-memory tiles, fused residual, temporal blocking */
+  PM_PATH_TILED = 2,  /* TMA-staged shared-memory tiles, fused residual, temporal blocking */
+  PM_PATH_PERSISTENT = 3 /* small grids: one persistent CTA runs the whole solve out of shared memory */
 } pm_kernel_path;
 
 typedef struct pm_config {

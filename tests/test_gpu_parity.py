@@ -344,3 +344,28 @@ def test_channel_profile_matches_reference_algorithm(pm, orc):
     assert prof.max() > 1.2 and prof.max() < 1.5 and prof.argmax() in (9, 10)
     yc = (np.arange(20) + 0.5) / 20
     assert np.abs(prof - 6 * yc * (1 - yc)).max() < 0.25
+
+
+@pytest.mark.parametrize("method,omega", [(JAC, 0.9), (RB, None)])
+@pytest.mark.parametrize("exact", [1, 0])
+@pytest.mark.parametrize("case_id,nx,ny", CASES + [(0, 128, 128), (1, 256, 64)])
+def test_persistent_small_grid_solve(pm, orc, case_id, nx, ny, method, omega, exact):
+    """The single-CTA persistent solve used for small grids (kernel_path = persistent): whole steps run to
+    the reference tolerance (cap 400) — iteration counts, residuals and all fields against the oracle,
+    0 ulp with exact arithmetic, 1e-12 relative with production arithmetic."""
+    cfg = make_cfg(pm, case_id, nx, ny, method, exact, 400, omega, path=3)
+    S, O = pm.Solver(cfg), orc.Oracle(cfg)
+    S.fill_random(23, 2.0 ** -6); O.fill_random(23, 2.0 ** -6)
+    S.apply_bc(0); O.apply_bc(0)
+    for n in range(2):
+        rs, ro = S.step(1), O.step(1)
+        if exact:
+            assert (rs.iterations, rs.residual) == (ro.iterations, ro.residual), f"step {n}"
+        else:
+            assert abs(rs.iterations - ro.iterations) <= 1
+    if exact:
+        assert_fields_equal(S, O, range(6), "persistent solve")
+    else:
+        for fid in range(6):
+            a, b = S.download(fid), O.field(fid)
+            assert np.abs(a - b).max() <= 1e-10 * max(1.0, np.abs(b).max()), f"field {fid}"
