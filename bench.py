@@ -25,7 +25,7 @@ sys.path.insert(0, os.path.join(ROOT, "computational-fluid-dynamics_b200"))
 
 METRIC = "Mcell-updates/s per projection step"
 UNIT = "Mcell-updates/s"
-K_ITERS = 100
+K_ITERS = 100  # headline; --k-iters overrides (K = 1 exposes the non-pressure passes)
 
 
 def bytes_per_cell_step(k):
@@ -81,7 +81,7 @@ def cpu_reference_rate(n, steps, warmup):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import orc
     name = f"cavity_k100_{n}"
-    if orc.ref_available(name):
+    if orc.ref_available(name) and K_ITERS == 100:
         R = orc.Reference(name)
         assert R.params()["max_iters"] == K_ITERS
         if warmup:
@@ -309,7 +309,10 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=1024)
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--ref-n", type=int, default=2048)
+    ap.add_argument("--k-iters", type=int, default=100, help="pressure iterations per step (max_iters cap)")
     args = ap.parse_args()
+    global K_ITERS
+    K_ITERS = args.k_iters
     if args.impl == "reference":
         run_reference(args)
     else:
