@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -46,6 +47,7 @@ struct pm_solver {
   int last_iters = 0;
   bool use_tiled = false;
   bool use_small = false;  // persistent single-CTA solve (small grids)
+  bool no_cluster = false; // PM_NO_CLUSTER=1 in the environment: keep the persistent solve on one SM
   int sweeps = 1;
   TiledPlan tiled{};
   PmNccl nccl{};
@@ -271,6 +273,7 @@ static int create_impl(pm_solver* s, const pm_config* cfg) {
                           size_t(c.nx) * size_t(c.ny) <= size_t(20) * 1024;
     if (c.kernel_path == PM_PATH_PERSISTENT && !small_ok)
       return fail(s, PM_ERR_UNSUPPORTED, "persistent path needs a single rank and a pressure field that fits shared memory");
+    s->no_cluster = std::getenv("PM_NO_CLUSTER") != nullptr;
     s->use_small = small_ok && !s->use_tiled && (c.kernel_path == PM_PATH_PERSISTENT || c.kernel_path == PM_PATH_AUTO);
   }
   if (s->use_tiled) {
@@ -785,9 +788,65 @@ static const void* small_kernel(const KP& k, int method) {
     return rb ? reinterpret_cast<const void*>(&k_ppe_small<A, 1, true, PM_PPE_SOR_RB>) : reinterpret_cast<const void*>(&k_ppe_small<A, 1, true, PM_PPE_JACOBI>);
   return rb ? reinterpret_cast<const void*>(&k_ppe_small<A, 1, false, PM_PPE_SOR_RB>) : reinterpret_cast<const void*>(&k_ppe_small<A, 1, false, PM_PPE_JACOBI>);
 }
-// Small grids: Jacobi / red-black in one persistent CTA (pm_kernels_lex.cuh, k_ppe_small).
+template <class A>
+static const void* cluster_kernel(const KP& k) {
+  if (k.case_id == PM_CASE_CAVITY) return reinterpret_cast<const void*>(&k_ppe_cluster<A, 0, false>);
+  if (k.has_mask) return reinterpret_cast<const void*>(&k_ppe_cluster<A, 1, true>);
+  return reinterpret_cast<const void*>(&k_ppe_cluster<A, 1, false>);
+}
+// Small grids, red-black: the persistent solve on a cluster of 8 CTAs with DSMEM halo rows (k_ppe_cluster).
+static int cluster_solve(pm_solver* s) {
+  const KP& k = s->kp;
+  const int nr_max = k.ny / PM_CLUSTER + (k.ny % PM_CLUSTER ? 1 : 0);
+  const size_t smem = size_t(2) * size_t(nr_max + 2) * size_t(k.nx + 2) * sizeof(double);
+  const void* kern = s->cfg.exact_arith ? cluster_kernel<Exact>(k) : cluster_kernel<Fast>(k);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const int cells = nr_max * k.nx;
+  const int threads = std::min(512, std::max(128, ((cells / 4 + 31) / 32) * 32));
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(PM_CLUSTER);
+  lc.blockDim = dim3(threads);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = s->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = PM_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  double* pg = s->pl[s->p_cur];
+  const double* f = s->pl[PL_F];
+  const uint8_t* m = s->mask;
+  PpeState* st = s->d_state;
+  unsigned long long* rb = s->d_res;
+  void* args[] = {(void*)&k, (void*)&pg, (void*)&f, (void*)&m, (void*)&st, (void*)&rb};
+  CK(cudaLaunchKernelExC(&lc, kern, args));
+  s->timing.kernel_launches++;
+  s->timing.ppe_passes++;
+  return PM_OK;
+}
+
+// Small grids: Jacobi / red-black in one persistent CTA (pm_kernels_lex.cuh, k_ppe_small), or red-black on a
+// cluster when the band of every CTA is at least two rows high and fits its shared memory.
 static int small_solve(pm_solver* s, int* iters_out, double* res_out) {
   const KP& k = s->kp;
+  {
+    const int nr_max = k.ny / PM_CLUSTER + (k.ny % PM_CLUSTER ? 1 : 0);
+    const size_t csmem = size_t(2) * size_t(nr_max + 2) * size_t(k.nx + 2) * sizeof(double);
+    if (s->cfg.ppe_method == PM_PPE_SOR_RB && k.ny >= 2 * PM_CLUSTER && csmem <= size_t(200) * 1024 && !s->no_cluster) {
+      PMTRY(cluster_solve(s));
+      PMTRY(read_state(s));
+      const int iters = s->h_state->iters;
+      if (iters >= 1) {
+        CK(cudaMemcpyAsync(s->h_res, s->d_res + iters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        std::memcpy(res_out, s->h_res, 8);
+      } else {
+        *res_out = s->h_state->res_init;
+      }
+      *iters_out = iters;
+      return PM_OK;
+    }
+  }
   const size_t smem = size_t(k.ny + 2) * size_t(k.nx + 2) * sizeof(double);
   const int cells = k.nx * k.ny;
   const int threads = std::min(1024, std::max(128, ((cells / 4 + 31) / 32) * 32));

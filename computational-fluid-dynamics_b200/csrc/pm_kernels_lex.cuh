@@ -233,3 +233,152 @@ __global__ void __launch_bounds__(1024, 1)
     if (it >= 1) res_bits[it] = (unsigned long long)__double_as_longlong(res);
   }
 }
+
+// ---------------------------------------------------------------------------
+// Small grids, red-black, on a thread-block CLUSTER: the same persistent solve spread over 8 SMs.
+// CTA c of the cluster owns a band of rows of p and f in its own shared memory plus one halo row above and
+// below; after each colour half-sweep the CTAs meet at a cluster barrier (barrier.cluster, ~0.2 us) and every
+// CTA copies the freshly updated colour of its two halo rows straight out of its neighbours' shared memory
+// (distributed shared memory).  Only the other colour is being written at that time, so one cluster barrier
+// per half-sweep suffices.  The per-CTA residual maxima are exchanged the same way and every CTA evaluates the
+// reference's loop test (cavity-01.cpp:635) on the same number, so the cluster leaves the loop together.
+// ---------------------------------------------------------------------------
+#include <cooperative_groups.h>
+namespace pm_cg = cooperative_groups;
+
+#define PM_CLUSTER 8
+
+__device__ __forceinline__ void pm_band(int ny, int c, int* ja, int* nr) {  // rows ja+1 .. ja+nr of the domain
+  const int base = ny / PM_CLUSTER, rem = ny % PM_CLUSTER;
+  *nr = base + (c < rem ? 1 : 0);
+  *ja = c * base + min(c, rem);
+}
+
+template <class A, int FORM, bool MASK>
+__global__ void __launch_bounds__(512, 1)
+    k_ppe_cluster(const __grid_constant__ KP k, double* pg, const double* __restrict__ f, const uint8_t* __restrict__ M,
+                  PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits) {
+  extern __shared__ double smem[];
+  __shared__ double red[32];
+  __shared__ double slot[2];  // this CTA's residual maximum, double-buffered by iteration parity
+  pm_cg::cluster_group cluster = pm_cg::this_cluster();
+  const int c = int(cluster.block_rank());
+  const int nx = k.nx, ny = k.ny, PP = nx + 2;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  int j0, nr;
+  pm_band(ny, c, &j0, &nr);
+  const int nr_max = ny / PM_CLUSTER + (ny % PM_CLUSTER ? 1 : 0);
+  double* P = smem;                          // local rows 0 .. nr+1  <->  domain rows j0 .. j0+nr+1
+  double* F = smem + size_t(nr_max + 2) * PP;  // local rows 1 .. nr (same indexing)
+  for (int idx = tid; idx < (nr + 2) * PP; idx += nth) {
+    const int l = idx / PP, i = idx - l * PP;
+    P[idx] = pg[pm_idx(k, j0 + l, i)];
+    F[idx] = (l >= 1 && l <= nr) ? f[pm_idx(k, j0 + l, i)] : 0.0;
+  }
+  // neighbours' tiles through distributed shared memory
+  const double* Pdn = c > 0 ? cluster.map_shared_rank(P, c - 1) : nullptr;
+  const double* Pup = c + 1 < PM_CLUSTER ? cluster.map_shared_rank(P, c + 1) : nullptr;
+  int nr_dn = 0, jdummy;
+  if (c > 0) pm_band(ny, c - 1, &jdummy, &nr_dn);
+  cluster.sync();
+
+  const int hw = (nx + 1) / 2;
+  // halo rows: local row 0 <- lower neighbour's top owned row; local row nr+1 <- upper neighbour's row 1.
+  auto pull_halo = [&](int colour /* -1: every cell */) {
+    for (int t = tid; t < 2 * nx; t += nth) {
+      const int up = t >= nx, i = 1 + (up ? t - nx : t);
+      const int j = up ? j0 + nr + 1 : j0;
+      if (colour >= 0 && ((i + j) & 1) != colour) continue;
+      if (!up && Pdn) P[i] = Pdn[size_t(nr_dn) * PP + i];
+      if (up && Pup) P[size_t(nr + 1) * PP + i] = Pup[size_t(PP) + i];
+    }
+    __syncthreads();
+  };
+  auto half_sweep = [&](int colour) {
+    for (int idx = tid; idx < nr * hw; idx += nth) {
+      const int l = 1 + idx / hw, j = j0 + l;
+      const int i = 1 + ((colour + j + 1) & 1) + 2 * (idx - (l - 1) * hw);
+      if (i > nx) continue;
+      if (MASK && !M[pm_idx(k, j, i)]) continue;
+      double* q = P + size_t(l) * PP + i;
+      const double fc = F[size_t(l) * PP + i];
+      const double r = FORM == 0 ? upd_cavity<A>(k, j, i, q[0], q[1], q[-1], q[PP], q[-PP], fc) : upd_channel<A>(k, q[0], q[1], q[-1], q[PP], q[-PP], fc);
+      q[0] = r;
+      if (FORM == 1 && !MASK) {  // wall ghosts owned by this cell (channel-01.cpp:531-541)
+        if (i == 1) q[-1] = r;
+        if (i == nx) q[1] = 0.0;
+        if (j == 1) q[-PP] = r;
+        if (j == ny) q[PP] = r;
+      }
+    }
+  };
+
+  const double tol = st->tol;
+  double res = st->res_init;
+  int it = 0;
+  while (res > tol && it < k.max_iters) {
+    ++it;
+    half_sweep(0);
+    cluster.sync();
+    pull_halo(0);
+    half_sweep(1);
+    cluster.sync();
+    pull_halo(1);
+    if (FORM == 1 && MASK) {  // backwards_step-01.cpp:685-740: wall ghosts first, then the solid cells
+      for (int t = 1 + tid; t <= max(nx, nr); t += nth) {
+        if (t <= nr) {
+          P[size_t(t) * PP] = P[size_t(t) * PP + 1];
+          P[size_t(t) * PP + nx + 1] = 0.0;
+        }
+        if (t <= nx) {
+          if (c == 0) P[t] = P[size_t(PP) + t];
+          if (c == PM_CLUSTER - 1) P[size_t(nr + 1) * PP + t] = P[size_t(nr) * PP + t];
+        }
+      }
+      __syncthreads();
+      for (int idx = tid; idx < nr * nx; idx += nth) {
+        const int l = 1 + idx / nx, i = 1 + idx - (l - 1) * nx, j = j0 + l;
+        const size_t g = pm_idx(k, j, i);
+        if (M[g]) continue;
+        double* q = P + size_t(l) * PP + i;
+        double s = 0.0;
+        int n = 0;
+        if (i > 1 && M[g - 1]) { s = __dadd_rn(s, q[-1]); ++n; }
+        if (i < nx && M[g + 1]) { s = __dadd_rn(s, q[1]); ++n; }
+        if (j > 1 && M[g - k.pitch]) { s = __dadd_rn(s, q[-PP]); ++n; }
+        if (j < ny && M[g + k.pitch]) { s = __dadd_rn(s, q[PP]); ++n; }
+        if (n > 0) q[0] = __ddiv_rn(s, double(n));
+      }
+      cluster.sync();
+      pull_halo(-1);  // solid cells of the neighbours' boundary rows changed too
+    }
+    double a = 0.0;
+    for (int idx = tid; idx < nr * nx; idx += nth) {
+      const int l = 1 + idx / nx, i = 1 + idx - (l - 1) * nx, j = j0 + l;
+      if (MASK && !M[pm_idx(k, j, i)]) continue;
+      const double* q = P + size_t(l) * PP + i;
+      const double fc = F[size_t(l) * PP + i];
+      const double r = FORM == 0 ? res_cavity<A>(k, j, i, q[0], q[1], q[-1], q[PP], q[-PP], fc, k.idx2) : res_channel<A>(k, q[0], q[1], q[-1], q[PP], q[-PP], fc);
+      a = fmax(a, fabs(r));
+    }
+    const double m = block_max(a, red);
+    if (tid == 0) slot[it & 1] = m;
+    cluster.sync();
+    double g = 0.0;
+    if ((tid & 31) < PM_CLUSTER) g = cluster.map_shared_rank(slot, tid & 31)[it & 1];
+    res = warp_max(g);  // every warp reads the 8 maxima itself, so all threads of the cluster see the same number
+  }
+  cluster.sync();  // nobody leaves while a neighbour may still read this CTA's shared memory
+
+  // write back the band, the wall-ghost columns, and the ghost rows the first / last CTA own
+  const int la = c == 0 ? 0 : 1, lb = c == PM_CLUSTER - 1 ? nr + 1 : nr;
+  for (int idx = tid; idx < (lb - la + 1) * PP; idx += nth) {
+    const int l = la + idx / PP, i = idx - (l - la) * PP;
+    pg[pm_idx(k, j0 + l, i)] = P[size_t(l) * PP + i];
+  }
+  if (c == 0 && tid == 0) {
+    st->iters = it;
+    st->done = 1;
+    if (it >= 1) res_bits[it] = (unsigned long long)__double_as_longlong(res);
+  }
+}

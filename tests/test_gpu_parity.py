@@ -346,13 +346,16 @@ def test_channel_profile_matches_reference_algorithm(pm, orc):
     assert np.abs(prof - 6 * yc * (1 - yc)).max() < 0.25
 
 
-@pytest.mark.parametrize("method,omega", [(JAC, 0.9), (RB, None)])
+@pytest.mark.parametrize("method,omega,one_sm", [(JAC, 0.9, False), (RB, None, False), (RB, None, True)])
 @pytest.mark.parametrize("exact", [1, 0])
-@pytest.mark.parametrize("case_id,nx,ny", CASES + [(0, 128, 128), (1, 256, 64)])
-def test_persistent_small_grid_solve(pm, orc, case_id, nx, ny, method, omega, exact):
-    """The single-CTA persistent solve used for small grids (kernel_path = persistent): whole steps run to
-    the reference tolerance (cap 400) — iteration counts, residuals and all fields against the oracle,
+@pytest.mark.parametrize("case_id,nx,ny", CASES + [(0, 128, 128), (1, 256, 64), (0, 37, 19)])
+def test_persistent_small_grid_solve(pm, orc, monkeypatch, case_id, nx, ny, method, omega, exact, one_sm):
+    """The persistent solves used for small grids (kernel_path = persistent; red-black: a cluster of 8 CTAs with
+    distributed-shared-memory halo rows, or one CTA; Jacobi: one CTA): whole steps run to the reference
+    tolerance (cap 400) — iteration counts, residuals and all fields against the oracle,
     0 ulp with exact arithmetic, 1e-12 relative with production arithmetic."""
+    if one_sm:
+        monkeypatch.setenv("PM_NO_CLUSTER", "1")  # red-black otherwise runs on a cluster of 8 CTAs with DSMEM halos
     cfg = make_cfg(pm, case_id, nx, ny, method, exact, 400, omega, path=3)
     S, O = pm.Solver(cfg), orc.Oracle(cfg)
     S.fill_random(23, 2.0 ** -6); O.fill_random(23, 2.0 ** -6)
