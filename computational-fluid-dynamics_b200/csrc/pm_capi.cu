@@ -702,7 +702,7 @@ static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
   }
   int m = 0, n = 0;
   bool done = false;
-  int chunk = s->cfg.poll_chunk > 0 ? s->cfg.poll_chunk : std::max(4, std::min(128, s->last_iters / (8 * T)));
+  int chunk = s->cfg.poll_chunk > 0 ? s->cfg.poll_chunk : std::max(4, std::min(128, s->last_iters / (2 * T)));
   while (m < K && !done) {
     int launched = 0;
     while (m < K && launched < chunk) {
@@ -893,10 +893,11 @@ extern "C" int pm_ppe_solve(pm_solver* s, pm_ppe_result* out) {
     std::string e;
     if (!pm_nccl_allreduce_max_u64(&s->nccl, s->stream, &s->d_state->maxf2_bits, 1, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
   }
-  if (cav) {  // cold start from p == 0, both buffers (cavity-01.cpp:610-611)
-    CK(cudaMemsetAsync(s->pl[PL_P0], 0, s->plane * sizeof(double), s->stream));
-    CK(cudaMemsetAsync(s->pl[PL_P1], 0, s->plane * sizeof(double), s->stream));
-    s->p_cur = PL_P0;
+  if (cav) {  // cold start from p == 0 (cavity-01.cpp:610-611)
+    // Only the buffer the solve starts from needs clearing: the first pass overwrites every interior cell of the
+    // other one, and in the cavity nothing ever writes a ghost or pad cell of either buffer (they stay 0 from
+    // pm_create / pm_fill_zero; halo rows between slabs are re-exchanged every pass).
+    CK(cudaMemsetAsync(s->pl[s->p_cur], 0, s->plane * sizeof(double), s->stream));
   }
   if (!cav && !s->use_small && (c.ppe_method == PM_PPE_JACOBI || s->use_tiled)) {  // ping-pong solves: both buffers carry the corner ghosts
     k_copy_corners<<<1, 32, 0, s->stream>>>(k, s->pl[s->p_cur], s->pl[s->p_cur == PL_P0 ? PL_P1 : PL_P0]);
