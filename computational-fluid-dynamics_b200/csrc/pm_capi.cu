@@ -303,6 +303,8 @@ extern "C" int pm_create(const pm_config* cfg, pm_solver** out) {
   if (cfg->case_id < PM_CASE_CAVITY || cfg->case_id > PM_CASE_STEP) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "unknown case %d", cfg->case_id);
   if (cfg->ppe_method < PM_PPE_JACOBI || cfg->ppe_method > PM_PPE_SOR_LEX) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "unknown ppe method %d", cfg->ppe_method);
   if (cfg->nx < 2 || cfg->ny < 2) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "grid must be at least 2x2");
+  if (cfg->kernel_path < PM_PATH_AUTO || cfg->kernel_path > PM_PATH_PERSISTENT) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "unknown kernel path %d", cfg->kernel_path);
+  if (cfg->sweeps_per_pass < 0 || cfg->sweeps_per_pass > 4) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "sweeps_per_pass out of range");
   if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "bad rank %d of %d", cfg->rank, cfg->nranks);
   if (cfg->max_iters < 0 || cfg->max_iters > (1 << 24)) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "max_iters out of range");
   // validateParameters, cavity-01.cpp:423-425

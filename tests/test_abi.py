@@ -89,3 +89,20 @@ def test_no_cpu_fallback(pm):
     assert b"no CPU path" in pm.lib().pm_last_error(None)
     with pytest.raises(pm.PmError):
         pm.Solver(cfg)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference: the reference's CPU code on a bounded sample; exactly one JSON line on stdout
+    with the contract's keys (the driver computes the GPU/CPU ratio from it)."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-n", "512"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "Mcell-updates/s per projection step" and d["unit"] == "Mcell-updates/s"
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["higher_is_better"] is True
