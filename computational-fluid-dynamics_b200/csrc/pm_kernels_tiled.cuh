@@ -22,6 +22,8 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdlib>
 #include <string>
 
 #include "pm_common.cuh"
@@ -345,45 +347,17 @@ __device__ __forceinline__ void run_sweeps(const KP& k, double* tpx, double* tpy
   if (lane == 0 && v > 0.0) atomicMax(&red[nloop], (unsigned long long)__double_as_longlong(v));
 }
 
+// Everything one CTA does for one tile once its TMA load has been issued on `bar`: masks, f loads, wait,
+// split-row rewrite, the sweeps, the 128-bit write-out and the per-iterate residual atomics.
 template <class A, int FORM, int METHOD, int T, int PAR0>
-__global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
-    k_ppe_tiled(const __grid_constant__ KP k, const __grid_constant__ CUtensorMap tmap_in, double* __restrict__ pout,
-                const double* __restrict__ f, PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits, int m0,
-                int nsw, int force, int tile_row0) {
+__device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t* bar, uint32_t phase, unsigned long long* red,
+                                             double* __restrict__ pout, const double* __restrict__ f,
+                                             unsigned long long* __restrict__ res_bits, int m0, int nsw, int bx, int by) {
   using C = TileCfg<METHOD, T>;
   constexpr int H = C::H, SW = C::SW, SH = C::SH, RPT = C::RPT, TX = C::TX, TY = C::TY;
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  double* tile = reinterpret_cast<double*>(smem_raw) + SW;  // one spare row above (and one below)
-  __shared__ __align__(8) uint64_t mbar;
-  __shared__ unsigned long long red[T + 1];  // bit patterns of the residual maxima of iterates m0 .. m0+T
-
   const int tid = threadIdx.x;
-  const int bx = blockIdx.x, by = blockIdx.y + tile_row0;
   const int x0 = 1 + bx * TX, y0 = 1 + by * TY;  // first output cell (i, jl)
   const int ib = x0 - H, jb = y0 - H;            // tile origin (i, jl)
-
-  // The tile load goes out before anything else; the loop test of the reference (which needs three
-  // dependent global loads) is evaluated while the TMA is in flight.
-  if (tid == 0) {
-    mbar_init(&mbar, 1);
-    fence_mbar_init();
-    mbar_expect_tx(&mbar, SH * SW * 8);
-    tma_load_2d(tile, &tmap_in, &mbar, PM_OFFC + ib, k.padr + jb);
-  }
-  if (tid <= T) red[tid] = 0ull;
-  __syncthreads();
-  if (!force) {
-    int first = -1;
-    if (tiled_stop(st, res_bits, m0, T, &first)) {
-      if (first >= 0 && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
-        st->iters = first;
-        st->done = 1;
-      }
-      mbar_wait(&mbar, 0);  // never leave with a bulk copy still landing in this CTA's shared memory
-      return;
-    }
-  }
-
   const int q = tid & 63, sg = tid >> 6;
   const int c0 = 2 * q, i0 = ib + c0;
   const int rr0 = sg * RPT;
@@ -407,11 +381,12 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
   // Every updatable cell of the tile strictly inside the domain (uniform over the block)?
   const bool interior = ib + 1 >= 2 && ib + SW - 2 <= k.nx - 1 && k.j0 + jb + 1 >= 2 && k.j0 + jb + SH - 2 <= k.ny - 1 &&
                         jb + SH - 1 <= k.nyl + H;
+  if (tid <= T) red[tid] = 0ull;  // ordered before the first shared atomic by the barriers below
 
   // f: HBM -> registers (or the thread's private shared-memory slots), 128-bit row loads, overlapping the TMA transfer of p
   Cells<RPT> c;
 #if PM_TILE_F_SMEM
-  double* fsw = reinterpret_cast<double*>(smem_raw) + (SH + 2) * SW + tid;
+  double* fsw = tile + (SH + 1) * SW + tid;  // behind the tile and its spare row
   c.fs = fsw;
 #define PM_PUT_F(r, vx, vy) do { fsw[(2 * (r)) * PM_TILE_THREADS] = (vx); fsw[(2 * (r) + 1) * PM_TILE_THREADS] = (vy); } while (0)
 #else
@@ -438,7 +413,7 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
     }
   }
 #undef PM_PUT_F
-  mbar_wait(&mbar, 0);
+  mbar_wait(bar, phase);
   {  // TMA delivered natural row order: take the own cells, then rewrite the tile in the split-row layout
     const double* tn = tile + rr0 * SW + c0;
 #pragma unroll
@@ -485,13 +460,100 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
   }
 
   // ---- residual norms: one global atomic per iterate and tile ----
-  __syncthreads();
+  __syncthreads();  // also: nobody touches the tile in shared memory after this point
   if (tid <= T) {
     const int m = m0 + tid;
     // Jacobi: red[t] is the full residual of iterate m0+t.  Red-black: red[t] collects the colour-0 part of
     // iterate m0+t (before sweep t+1 replaces it) and the colour-1 part taken right after sweep t created it.
     const unsigned long long v = red[tid];
     if (v != 0ull && m >= 1 && m <= k.max_iters) atomicMax(&res_bits[m], v);
+  }
+}
+
+// One tile per CTA, two CTAs per SM: one CTA's loads overlap the other's sweeps.
+template <class A, int FORM, int METHOD, int T, int PAR0>
+__global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
+    k_ppe_tiled(const __grid_constant__ KP k, const __grid_constant__ CUtensorMap tmap_in, double* __restrict__ pout,
+                const double* __restrict__ f, PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits, int m0,
+                int nsw, int force, int tile_row0) {
+  using C = TileCfg<METHOD, T>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  double* tile = reinterpret_cast<double*>(smem_raw) + C::SW;  // one spare row above (and one below)
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ unsigned long long red[T + 1];  // bit patterns of the residual maxima of iterates m0 .. m0+T
+
+  const int tid = threadIdx.x;
+  const int bx = blockIdx.x, by = blockIdx.y + tile_row0;
+  // The tile load goes out before anything else; the loop test of the reference (which needs three
+  // dependent global loads) is evaluated while the TMA is in flight.
+  if (tid == 0) {
+    mbar_init(&mbar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(&mbar, C::SH * C::SW * 8);
+    tma_load_2d(tile, &tmap_in, &mbar, PM_OFFC + 1 + bx * C::TX - C::H, k.padr + 1 + by * C::TY - C::H);
+  }
+  __syncthreads();
+  if (!force) {
+    int first = -1;
+    if (tiled_stop(st, res_bits, m0, T, &first)) {
+      if (first >= 0 && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+        st->iters = first;
+        st->done = 1;
+      }
+      mbar_wait(&mbar, 0);  // never leave with a bulk copy still landing in this CTA's shared memory
+      return;
+    }
+  }
+  tile_process<A, FORM, METHOD, T, PAR0>(k, tile, &mbar, 0u, red, pout, f, res_bits, m0, nsw, bx, by);
+}
+
+// Experimental: persistent CTAs (two per SM) that walk the tiles of the launch with the TMA load of the NEXT
+// tile in flight while the current one is swept (double-buffered tile, two mbarriers with alternating phase).
+template <class A, int FORM, int METHOD, int T, int PAR0>
+__global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
+    k_ppe_tiled_persistent(const __grid_constant__ KP k, const __grid_constant__ CUtensorMap tmap_in, double* __restrict__ pout,
+                           const double* __restrict__ f, PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits, int m0,
+                           int nsw, int force, int tile_row0, int tiles_x, int ntiles) {
+  using C = TileCfg<METHOD, T>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int BUF = (C::SH + 2) * C::SW;  // doubles per buffer incl. the spare rows
+  double* base = reinterpret_cast<double*>(smem_raw);
+  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ unsigned long long red[T + 1];
+  const int tid = threadIdx.x;
+  if (!force) {
+    int first = -1;
+    if (tiled_stop(st, res_bits, m0, T, &first)) {
+      if (first >= 0 && blockIdx.x == 0 && tid == 0) {
+        st->iters = first;
+        st->done = 1;
+      }
+      return;
+    }
+  }
+  auto issue = [&](int L, int b) {  // thread 0: arm barrier b and start the tile load of linear tile L into buffer b
+    const int bx = L % tiles_x, by = tile_row0 + L / tiles_x;
+    mbar_expect_tx(&mbar[b], C::SH * C::SW * 8);
+    tma_load_2d(base + b * BUF + C::SW, &tmap_in, &mbar[b], PM_OFFC + 1 + bx * C::TX - C::H, k.padr + 1 + by * C::TY - C::H);
+  };
+  int L = blockIdx.x;
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+    if (L < ntiles) issue(L, 0);
+  }
+  __syncthreads();
+  for (int n = 0; L < ntiles; ++n, L += gridDim.x) {
+    const int b = n & 1;
+    if (tid == 0 && L + int(gridDim.x) < ntiles) {
+      // buffer b^1 was last touched (generic proxy) before the barrier that ended the previous tile
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(L + gridDim.x, b ^ 1);
+    }
+    tile_process<A, FORM, METHOD, T, PAR0>(k, base + b * BUF + C::SW, &mbar[b], uint32_t((n >> 1) & 1), red, pout, f, res_bits, m0, nsw,
+                                            L % tiles_x, tile_row0 + L / tiles_x);
+    __syncthreads();
   }
 }
 
@@ -507,6 +569,8 @@ struct TiledPlan {
   CUtensorMap map[2];   // p ping / p pong
   double* p[2] = {nullptr, nullptr};
   const void* kernel = nullptr;
+  const void* kernel_persistent = nullptr;  // experimental (PM_TILED_PERSISTENT=1)
+  int persistent = 0, persistent_grid = 0;
 };
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -521,7 +585,9 @@ static inline bool tiled_supported(const pm_config& c, const KP& k) {
 }
 
 template <class A, int FORM, int METHOD, int T>
-static const void* tiled_kernel_ptr(int par0) {
+static const void* tiled_kernel_ptr(int par0, const void** persistent) {
+  *persistent = par0 ? reinterpret_cast<const void*>(&k_ppe_tiled_persistent<A, FORM, METHOD, T, 1>)
+                     : reinterpret_cast<const void*>(&k_ppe_tiled_persistent<A, FORM, METHOD, T, 0>);
   return par0 ? reinterpret_cast<const void*>(&k_ppe_tiled<A, FORM, METHOD, T, 1>) : reinterpret_cast<const void*>(&k_ppe_tiled<A, FORM, METHOD, T, 0>);
 }
 
@@ -535,15 +601,15 @@ template <class A, int FORM>
 static const void* tiled_pick(int method, int T, int par0, TiledPlan* pl) {
   if (method == PM_PPE_SOR_RB) {
     switch (T) {
-      case 1: tiled_geometry<PM_PPE_SOR_RB, 1>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 1>(par0);
-      case 2: tiled_geometry<PM_PPE_SOR_RB, 2>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 2>(par0);
-      case 3: tiled_geometry<PM_PPE_SOR_RB, 3>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 3>(par0);
+      case 1: tiled_geometry<PM_PPE_SOR_RB, 1>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 1>(par0, &pl->kernel_persistent);
+      case 2: tiled_geometry<PM_PPE_SOR_RB, 2>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 2>(par0, &pl->kernel_persistent);
+      case 3: tiled_geometry<PM_PPE_SOR_RB, 3>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 3>(par0, &pl->kernel_persistent);
     }
   } else {
     switch (T) {
-      case 1: tiled_geometry<PM_PPE_JACOBI, 1>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 1>(par0);
-      case 2: tiled_geometry<PM_PPE_JACOBI, 2>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 2>(par0);
-      case 4: tiled_geometry<PM_PPE_JACOBI, 4>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 4>(par0);
+      case 1: tiled_geometry<PM_PPE_JACOBI, 1>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 1>(par0, &pl->kernel_persistent);
+      case 2: tiled_geometry<PM_PPE_JACOBI, 2>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 2>(par0, &pl->kernel_persistent);
+      case 4: tiled_geometry<PM_PPE_JACOBI, 4>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 4>(par0, &pl->kernel_persistent);
     }
   }
   return nullptr;
@@ -578,6 +644,15 @@ static inline bool tiled_create(TiledPlan* pl, const pm_config& c, const KP& k, 
   }
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes);
   if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return false; }
+  pl->persistent = std::getenv("PM_TILED_PERSISTENT") != nullptr;
+  if (pl->persistent) {
+    e = cudaFuncSetAttribute(pl->kernel_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * pl->smem_bytes);
+    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute (persistent): ") + cudaGetErrorString(e); return false; }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    pl->persistent_grid = 2 * sms;
+  }
   return true;
 }
 static inline void tiled_destroy(TiledPlan*) {}
@@ -586,6 +661,13 @@ static inline void tiled_destroy(TiledPlan*) {}
 static inline cudaError_t tiled_launch(const TiledPlan* pl, const KP& k, int in, const double* f, PpeState* st, unsigned long long* res,
                                        int m0, int nsw, int force, int tile_row0, int tile_rows, cudaStream_t stream) {
   double* pout = pl->p[in ^ 1];
+  if (pl->persistent) {
+    int tiles_x = pl->tiles_x, ntiles = pl->tiles_x * tile_rows;
+    void* pargs[] = {(void*)&k, (void*)&pl->map[in], (void*)&pout, (void*)&f, (void*)&st, (void*)&res,
+                     (void*)&m0, (void*)&nsw, (void*)&force, (void*)&tile_row0, (void*)&tiles_x, (void*)&ntiles};
+    return cudaLaunchKernel(pl->kernel_persistent, dim3(std::min(ntiles, pl->persistent_grid)), dim3(PM_TILE_THREADS), pargs,
+                            size_t(2 * pl->smem_bytes), stream);
+  }
   void* args[] = {(void*)&k, (void*)&pl->map[in], (void*)&pout, (void*)&f, (void*)&st, (void*)&res,
                   (void*)&m0, (void*)&nsw, (void*)&force, (void*)&tile_row0};
   return cudaLaunchKernel(pl->kernel, dim3(pl->tiles_x, tile_rows), dim3(PM_TILE_THREADS), args, size_t(pl->smem_bytes), stream);
