@@ -507,56 +507,6 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
   tile_process<A, FORM, METHOD, T, PAR0>(k, tile, &mbar, 0u, red, pout, f, res_bits, m0, nsw, bx, by);
 }
 
-// Experimental: persistent CTAs (two per SM) that walk the tiles of the launch with the TMA load of the NEXT
-// tile in flight while the current one is swept (double-buffered tile, two mbarriers with alternating phase).
-template <class A, int FORM, int METHOD, int T, int PAR0>
-__global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
-    k_ppe_tiled_persistent(const __grid_constant__ KP k, const __grid_constant__ CUtensorMap tmap_in, double* __restrict__ pout,
-                           const double* __restrict__ f, PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits, int m0,
-                           int nsw, int force, int tile_row0, int tiles_x, int ntiles) {
-  using C = TileCfg<METHOD, T>;
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  constexpr int BUF = (C::SH + 2) * C::SW;  // doubles per buffer incl. the spare rows
-  double* base = reinterpret_cast<double*>(smem_raw);
-  __shared__ __align__(8) uint64_t mbar[2];
-  __shared__ unsigned long long red[T + 1];
-  const int tid = threadIdx.x;
-  if (!force) {
-    int first = -1;
-    if (tiled_stop(st, res_bits, m0, T, &first)) {
-      if (first >= 0 && blockIdx.x == 0 && tid == 0) {
-        st->iters = first;
-        st->done = 1;
-      }
-      return;
-    }
-  }
-  auto issue = [&](int L, int b) {  // thread 0: arm barrier b and start the tile load of linear tile L into buffer b
-    const int bx = L % tiles_x, by = tile_row0 + L / tiles_x;
-    mbar_expect_tx(&mbar[b], C::SH * C::SW * 8);
-    tma_load_2d(base + b * BUF + C::SW, &tmap_in, &mbar[b], PM_OFFC + 1 + bx * C::TX - C::H, k.padr + 1 + by * C::TY - C::H);
-  };
-  int L = blockIdx.x;
-  if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
-    fence_mbar_init();
-    if (L < ntiles) issue(L, 0);
-  }
-  __syncthreads();
-  for (int n = 0; L < ntiles; ++n, L += gridDim.x) {
-    const int b = n & 1;
-    if (tid == 0 && L + int(gridDim.x) < ntiles) {
-      // buffer b^1 was last touched (generic proxy) before the barrier that ended the previous tile
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(L + gridDim.x, b ^ 1);
-    }
-    tile_process<A, FORM, METHOD, T, PAR0>(k, base + b * BUF + C::SW, &mbar[b], uint32_t((n >> 1) & 1), red, pout, f, res_bits, m0, nsw,
-                                            L % tiles_x, tile_row0 + L / tiles_x);
-    __syncthreads();
-  }
-}
-
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -569,8 +519,6 @@ struct TiledPlan {
   CUtensorMap map[2];   // p ping / p pong
   double* p[2] = {nullptr, nullptr};
   const void* kernel = nullptr;
-  const void* kernel_persistent = nullptr;  // experimental (PM_TILED_PERSISTENT=1)
-  int persistent = 0, persistent_grid = 0;
 };
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -585,9 +533,7 @@ static inline bool tiled_supported(const pm_config& c, const KP& k) {
 }
 
 template <class A, int FORM, int METHOD, int T>
-static const void* tiled_kernel_ptr(int par0, const void** persistent) {
-  *persistent = par0 ? reinterpret_cast<const void*>(&k_ppe_tiled_persistent<A, FORM, METHOD, T, 1>)
-                     : reinterpret_cast<const void*>(&k_ppe_tiled_persistent<A, FORM, METHOD, T, 0>);
+static const void* tiled_kernel_ptr(int par0) {
   return par0 ? reinterpret_cast<const void*>(&k_ppe_tiled<A, FORM, METHOD, T, 1>) : reinterpret_cast<const void*>(&k_ppe_tiled<A, FORM, METHOD, T, 0>);
 }
 
@@ -601,15 +547,15 @@ template <class A, int FORM>
 static const void* tiled_pick(int method, int T, int par0, TiledPlan* pl) {
   if (method == PM_PPE_SOR_RB) {
     switch (T) {
-      case 1: tiled_geometry<PM_PPE_SOR_RB, 1>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 1>(par0, &pl->kernel_persistent);
-      case 2: tiled_geometry<PM_PPE_SOR_RB, 2>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 2>(par0, &pl->kernel_persistent);
-      case 3: tiled_geometry<PM_PPE_SOR_RB, 3>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 3>(par0, &pl->kernel_persistent);
+      case 1: tiled_geometry<PM_PPE_SOR_RB, 1>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 1>(par0);
+      case 2: tiled_geometry<PM_PPE_SOR_RB, 2>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 2>(par0);
+      case 3: tiled_geometry<PM_PPE_SOR_RB, 3>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 3>(par0);
     }
   } else {
     switch (T) {
-      case 1: tiled_geometry<PM_PPE_JACOBI, 1>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 1>(par0, &pl->kernel_persistent);
-      case 2: tiled_geometry<PM_PPE_JACOBI, 2>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 2>(par0, &pl->kernel_persistent);
-      case 4: tiled_geometry<PM_PPE_JACOBI, 4>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 4>(par0, &pl->kernel_persistent);
+      case 1: tiled_geometry<PM_PPE_JACOBI, 1>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 1>(par0);
+      case 2: tiled_geometry<PM_PPE_JACOBI, 2>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 2>(par0);
+      case 4: tiled_geometry<PM_PPE_JACOBI, 4>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_JACOBI, 4>(par0);
     }
   }
   return nullptr;
@@ -644,15 +590,6 @@ static inline bool tiled_create(TiledPlan* pl, const pm_config& c, const KP& k, 
   }
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes);
   if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return false; }
-  pl->persistent = std::getenv("PM_TILED_PERSISTENT") != nullptr;
-  if (pl->persistent) {
-    e = cudaFuncSetAttribute(pl->kernel_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * pl->smem_bytes);
-    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute (persistent): ") + cudaGetErrorString(e); return false; }
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    pl->persistent_grid = 2 * sms;
-  }
   return true;
 }
 static inline void tiled_destroy(TiledPlan*) {}
@@ -661,13 +598,6 @@ static inline void tiled_destroy(TiledPlan*) {}
 static inline cudaError_t tiled_launch(const TiledPlan* pl, const KP& k, int in, const double* f, PpeState* st, unsigned long long* res,
                                        int m0, int nsw, int force, int tile_row0, int tile_rows, cudaStream_t stream) {
   double* pout = pl->p[in ^ 1];
-  if (pl->persistent) {
-    int tiles_x = pl->tiles_x, ntiles = pl->tiles_x * tile_rows;
-    void* pargs[] = {(void*)&k, (void*)&pl->map[in], (void*)&pout, (void*)&f, (void*)&st, (void*)&res,
-                     (void*)&m0, (void*)&nsw, (void*)&force, (void*)&tile_row0, (void*)&tiles_x, (void*)&ntiles};
-    return cudaLaunchKernel(pl->kernel_persistent, dim3(std::min(ntiles, pl->persistent_grid)), dim3(PM_TILE_THREADS), pargs,
-                            size_t(2 * pl->smem_bytes), stream);
-  }
   void* args[] = {(void*)&k, (void*)&pl->map[in], (void*)&pout, (void*)&f, (void*)&st, (void*)&res,
                   (void*)&m0, (void*)&nsw, (void*)&force, (void*)&tile_row0};
   return cudaLaunchKernel(pl->kernel, dim3(pl->tiles_x, tile_rows), dim3(PM_TILE_THREADS), args, size_t(pl->smem_bytes), stream);
