@@ -261,21 +261,21 @@ static int create_impl(pm_solver* s, const pm_config* cfg) {
     PMTRY(upload_mask_rows(s, m.data()));
   }
 
-  // kernel path
+  // kernel path.  AUTO: small grids -> the persistent cluster / single-CTA solve; every other unmasked
+  // Jacobi / red-black problem -> the TMA-tiled kernel; the rest (obstacle mask beyond the small-grid limit)
+  // -> the general kernels.
   const bool tiled_ok = tiled_supported(c, k);
   if (c.kernel_path == PM_PATH_TILED && !tiled_ok)
     return fail(s, PM_ERR_UNSUPPORTED, "tiled path supports unmasked jacobi / sor-rb only");
-  s->use_tiled = tiled_ok && c.ppe_method != PM_PPE_SOR_LEX && (c.kernel_path == PM_PATH_TILED ||
-                              (c.kernel_path == PM_PATH_AUTO && size_t(c.nx) * size_t(nyl) >= (size_t(1) << 18)));
-  {
-    const size_t bytes = size_t(c.ny + 2) * size_t(c.nx + 2) * sizeof(double);
-    const bool small_ok = c.nranks == 1 && c.ppe_method != PM_PPE_SOR_LEX && bytes <= size_t(200) * 1024 &&
-                          size_t(c.nx) * size_t(c.ny) <= size_t(20) * 1024;
-    if (c.kernel_path == PM_PATH_PERSISTENT && !small_ok)
-      return fail(s, PM_ERR_UNSUPPORTED, "persistent path needs a single rank and a pressure field that fits shared memory");
-    s->no_cluster = std::getenv("PM_NO_CLUSTER") != nullptr;
-    s->use_small = small_ok && !s->use_tiled && (c.kernel_path == PM_PATH_PERSISTENT || c.kernel_path == PM_PATH_AUTO);
-  }
+  const size_t pbytes = size_t(c.ny + 2) * size_t(c.nx + 2) * sizeof(double);
+  const bool small_ok = c.nranks == 1 && c.ppe_method != PM_PPE_SOR_LEX && pbytes <= size_t(200) * 1024 &&
+                        size_t(c.nx) * size_t(c.ny) <= size_t(20) * 1024;
+  if (c.kernel_path == PM_PATH_PERSISTENT && !small_ok)
+    return fail(s, PM_ERR_UNSUPPORTED, "persistent path needs a single rank and a pressure field that fits shared memory");
+  s->no_cluster = std::getenv("PM_NO_CLUSTER") != nullptr;
+  s->use_small = small_ok && (c.kernel_path == PM_PATH_PERSISTENT || c.kernel_path == PM_PATH_AUTO);
+  s->use_tiled = tiled_ok && !s->use_small && c.ppe_method != PM_PPE_SOR_LEX &&
+                 (c.kernel_path == PM_PATH_TILED || (c.kernel_path == PM_PATH_AUTO && (c.nranks == 1 || nyl >= 2 * PM_PADR)));
   if (s->use_tiled) {
     std::string e;
     if (!tiled_create(&s->tiled, c, k, s->pl[PL_P0], s->pl[PL_P1], s->rows_alloc, &e))

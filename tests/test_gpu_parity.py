@@ -372,3 +372,16 @@ def test_persistent_small_grid_solve(pm, orc, monkeypatch, case_id, nx, ny, meth
         for fid in range(6):
             a, b = S.download(fid), O.field(fid)
             assert np.abs(a - b).max() <= 1e-10 * max(1.0, np.abs(b).max()), f"field {fid}"
+
+
+@pytest.mark.parametrize("case_id,nx,ny,method", [(0, 300, 200, RB), (1, 260, 180, RB), (0, 300, 200, JAC), (2, 300, 90, RB)])
+def test_auto_path_mid_size_bit_exact(pm, orc, case_id, nx, ny, method):
+    """kernel_path = auto on grids between the small-grid limit and the benchmark sizes (tiled kernel with few
+    tiles; general kernels for the masked step case): one whole step against the oracle, 0 ulp."""
+    cfg = make_cfg(pm, case_id, nx, ny, method, 1, 20, 0.9 if method == JAC else None, path=0)
+    S, O = pm.Solver(cfg), orc.Oracle(cfg)
+    S.fill_random(31, 2.0 ** -5); O.fill_random(31, 2.0 ** -5)
+    S.apply_bc(0); O.apply_bc(0)
+    rs, ro = S.step(1), O.step(1)
+    assert (rs.iterations, rs.residual) == (ro.iterations, ro.residual)
+    assert_fields_equal(S, O, range(6), "auto path")
