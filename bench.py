@@ -41,30 +41,37 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (one streaming nvidia-smi process,
+    a row every 50 ms; rows are timestamped on arrival and only those inside [start, stop] are kept)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.rows, self.proc = index, [], None
+        self.t_start = self.t_stop = None
 
     def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.02)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+        except Exception:
+            pass
+
+    def mark_start(self):
+        self.t_start = time.perf_counter()
 
     def stop(self):
-        self._stop_evt.set()
+        self.t_stop = time.perf_counter()
+        time.sleep(0.12)  # let the last rows of the region arrive
+        if self.proc is not None:
+            self.proc.terminate()
         self.join(timeout=5)
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        rows = [r for t, r in self.rows if self.t_start is None or self.t_start <= t <= self.t_stop + 0.1] or [r for _, r in self.rows]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
             except Exception:
@@ -185,7 +192,10 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        time.sleep(0.3)  # nvidia-smi needs a moment to start streaming
     barrier()
+    if sampler:
+        sampler.mark_start()
     S.timer_start()
     for _ in range(args.steps):
         r = S.step(1)
