@@ -385,3 +385,43 @@ def test_auto_path_mid_size_bit_exact(pm, orc, case_id, nx, ny, method):
     rs, ro = S.step(1), O.step(1)
     assert (rs.iterations, rs.residual) == (ro.iterations, ro.residual)
     assert_fields_equal(S, O, range(6), "auto path")
+
+
+@pytest.mark.parametrize("path", [1, 3, 2])
+@pytest.mark.parametrize("case_id,nx,ny", [(0, 2, 2), (0, 3, 5), (1, 2, 3), (1, 5, 2), (2, 6, 4), (0, 116, 28), (0, 117, 29), (1, 129, 45), (0, 127, 17)])
+def test_ragged_and_tiny_grids_bit_exact(pm, orc, case_id, nx, ny, path):
+    """Edge sizes: the smallest legal grids, odd extents (column pairs straddling the east wall), grids of exactly
+    one output tile and one cell more — through the general, persistent and tiled paths."""
+    if path == 2 and case_id == 2:
+        pytest.skip("the masked step case has no tiled path")
+    cfg = make_cfg(pm, case_id, nx, ny, RB, 1, 12, path=path)
+    if case_id == 2:
+        cfg.step_i_location, cfg.inlet_j_max = 2, 2
+    cfg.sweeps_per_pass = 3 if path == 2 else 0
+    S, O = pm.Solver(cfg), orc.Oracle(cfg)
+    S.fill_random(77); O.fill_random(77)
+    S.apply_bc(0); O.apply_bc(0)
+    rs, ro = S.step(2), O.step(2)
+    assert (rs.iterations, rs.residual) == (ro.iterations, ro.residual)
+    assert_fields_equal(S, O, range(6), "ragged/tiny")
+
+
+@pytest.mark.parametrize("path", [1, 2, 3])
+def test_loop_entry_quirks(pm, orc, path):
+    """max_iters = 0 and the cavity's loop-entry rule: the reference starts its residual at
+    1.0, so a source with 1e-9*max|f| >= 1 makes it skip the solve and return p == 0 after 0 iterations."""
+    cfg = make_cfg(pm, 0, 130, 40, RB, 1, 0, path=path)
+    cfg.sweeps_per_pass = 2 if path == 2 else 0
+    S, O = pm.Solver(cfg), orc.Oracle(cfg)
+    S.fill_random(3); O.fill_random(3)
+    rs, ro = S.step(1), O.step(1)
+    assert rs.iterations == ro.iterations == 0 and rs.residual == ro.residual == 1.0
+    assert_fields_equal(S, O, range(6), "max_iters=0")
+    cfg = make_cfg(pm, 0, 130, 40, RB, 1, 50, path=path)
+    cfg.sweeps_per_pass = 2 if path == 2 else 0
+    S, O = pm.Solver(cfg), orc.Oracle(cfg)
+    S.fill_random(3, 2.0 ** 14); O.fill_random(3, 2.0 ** 14)   # max|f| ~ 1e12 -> tolerance ~ 1e3 >= 1
+    rs, ro = S.step(1), O.step(1)
+    assert ro.tolerance >= 1.0 and rs.iterations == ro.iterations == 0
+    assert not S.download(2).any()
+    assert_fields_equal(S, O, range(6), "loop skipped")
