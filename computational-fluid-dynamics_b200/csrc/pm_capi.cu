@@ -800,11 +800,12 @@ static const void* cluster_kernel(const KP& k) {
 static int cluster_solve(pm_solver* s) {
   const KP& k = s->kp;
   const int nr_max = k.ny / PM_CLUSTER + (k.ny % PM_CLUSTER ? 1 : 0);
-  const size_t smem = size_t(2) * size_t(nr_max + 2) * size_t(k.nx + 2) * sizeof(double);
+  const size_t smem = size_t(nr_max + 2) * size_t(k.nx + 2) * sizeof(double);
   const void* kern = s->cfg.exact_arith ? cluster_kernel<Exact>(k) : cluster_kernel<Fast>(k);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  const int cells = nr_max * k.nx;
-  const int threads = std::min(512, std::max(128, ((cells / 4 + 31) / 32) * 32));
+  // each thread keeps up to PM_CLUSTER_CPT cells per colour: enough threads for the band's half rows
+  const int per_colour = nr_max * ((k.nx + 1) / 2);
+  const int threads = std::min(512, std::max(64, (((per_colour + PM_CLUSTER_CPT - 1) / PM_CLUSTER_CPT + 31) / 32) * 32));
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3(PM_CLUSTER);
   lc.blockDim = dim3(threads);
@@ -833,8 +834,9 @@ static int small_solve(pm_solver* s, int* iters_out, double* res_out) {
   const KP& k = s->kp;
   {
     const int nr_max = k.ny / PM_CLUSTER + (k.ny % PM_CLUSTER ? 1 : 0);
-    const size_t csmem = size_t(2) * size_t(nr_max + 2) * size_t(k.nx + 2) * sizeof(double);
-    if (s->cfg.ppe_method == PM_PPE_SOR_RB && k.ny >= 2 * PM_CLUSTER && csmem <= size_t(200) * 1024 && !s->no_cluster) {
+    const size_t csmem = size_t(nr_max + 2) * size_t(k.nx + 2) * sizeof(double);
+    const bool fits = nr_max * ((k.nx + 1) / 2) <= 512 * PM_CLUSTER_CPT;  // cells per colour and CTA held in registers
+    if (s->cfg.ppe_method == PM_PPE_SOR_RB && k.ny >= 2 * PM_CLUSTER && csmem <= size_t(200) * 1024 && fits && !s->no_cluster) {
       PMTRY(cluster_solve(s));
       PMTRY(read_state(s));
       const int iters = s->h_state->iters;

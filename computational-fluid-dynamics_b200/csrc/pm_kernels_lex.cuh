@@ -254,6 +254,8 @@ __device__ __forceinline__ void pm_band(int ny, int c, int* ja, int* nr) {  // r
   *ja = c * base + min(c, rem);
 }
 
+#define PM_CLUSTER_CPT 4  // cells per thread and colour (512 threads x 4 x 2 colours x 8 CTAs = 32 K cells)
+
 template <class A, int FORM, bool MASK>
 __global__ void __launch_bounds__(512, 1)
     k_ppe_cluster(const __grid_constant__ KP k, double* pg, const double* __restrict__ f, const uint8_t* __restrict__ M,
@@ -267,22 +269,41 @@ __global__ void __launch_bounds__(512, 1)
   const int tid = threadIdx.x, nth = blockDim.x;
   int j0, nr;
   pm_band(ny, c, &j0, &nr);
-  const int nr_max = ny / PM_CLUSTER + (ny % PM_CLUSTER ? 1 : 0);
-  double* P = smem;                          // local rows 0 .. nr+1  <->  domain rows j0 .. j0+nr+1
-  double* F = smem + size_t(nr_max + 2) * PP;  // local rows 1 .. nr (same indexing)
+  double* P = smem;  // local rows 0 .. nr+1  <->  domain rows j0 .. j0+nr+1
   for (int idx = tid; idx < (nr + 2) * PP; idx += nth) {
     const int l = idx / PP, i = idx - l * PP;
     P[idx] = pg[pm_idx(k, j0 + l, i)];
-    F[idx] = (l >= 1 && l <= nr) ? f[pm_idx(k, j0 + l, i)] : 0.0;
   }
   // neighbours' tiles through distributed shared memory
   const double* Pdn = c > 0 ? cluster.map_shared_rank(P, c - 1) : nullptr;
   const double* Pup = c + 1 < PM_CLUSTER ? cluster.map_shared_rank(P, c + 1) : nullptr;
   int nr_dn = 0, jdummy;
   if (c > 0) pm_band(ny, c - 1, &jdummy, &nr_dn);
+
+  // The cells this thread relaxes, fixed for the whole solve: per colour up to PM_CLUSTER_CPT cells with their
+  // shared-memory offset, their (j, i) and their source value in registers, so an iteration is nothing but
+  // loads, the reference's expression tree and one store per cell (no index arithmetic in the loop).
+  const int hw = (nx + 1) / 2;
+  int off[2][PM_CLUSTER_CPT], ji[2][PM_CLUSTER_CPT];
+  double fv[2][PM_CLUSTER_CPT];
+#pragma unroll
+  for (int colour = 0; colour < 2; ++colour)
+#pragma unroll
+    for (int q = 0; q < PM_CLUSTER_CPT; ++q) {
+      const int idx = tid + q * nth;
+      off[colour][q] = -1; ji[colour][q] = 0; fv[colour][q] = 0.0;
+      if (idx < nr * hw) {
+        const int l = 1 + idx / hw, j = j0 + l;
+        const int i = 1 + ((colour + j + 1) & 1) + 2 * (idx - (l - 1) * hw);
+        if (i <= nx && (!MASK || M[pm_idx(k, j, i)])) {
+          off[colour][q] = l * PP + i;
+          ji[colour][q] = (j << 16) | i;
+          fv[colour][q] = f[pm_idx(k, j, i)];
+        }
+      }
+    }
   cluster.sync();
 
-  const int hw = (nx + 1) / 2;
   // halo rows: local row 0 <- lower neighbour's top owned row; local row nr+1 <- upper neighbour's row 1.
   auto pull_halo = [&](int colour /* -1: every cell */) {
     for (int t = tid; t < 2 * nx; t += nth) {
@@ -295,20 +316,21 @@ __global__ void __launch_bounds__(512, 1)
     __syncthreads();
   };
   auto half_sweep = [&](int colour) {
-    for (int idx = tid; idx < nr * hw; idx += nth) {
-      const int l = 1 + idx / hw, j = j0 + l;
-      const int i = 1 + ((colour + j + 1) & 1) + 2 * (idx - (l - 1) * hw);
-      if (i > nx) continue;
-      if (MASK && !M[pm_idx(k, j, i)]) continue;
-      double* q = P + size_t(l) * PP + i;
-      const double fc = F[size_t(l) * PP + i];
-      const double r = FORM == 0 ? upd_cavity<A>(k, j, i, q[0], q[1], q[-1], q[PP], q[-PP], fc) : upd_channel<A>(k, q[0], q[1], q[-1], q[PP], q[-PP], fc);
-      q[0] = r;
+#pragma unroll
+    for (int q = 0; q < PM_CLUSTER_CPT; ++q) {
+      const int o = colour ? off[1][q] : off[0][q];
+      if (o < 0) continue;
+      const int jj = colour ? ji[1][q] : ji[0][q];
+      const int j = jj >> 16, i = jj & 0xffff;
+      const double fc = colour ? fv[1][q] : fv[0][q];
+      double* qd = P + o;
+      const double r = FORM == 0 ? upd_cavity<A>(k, j, i, qd[0], qd[1], qd[-1], qd[PP], qd[-PP], fc) : upd_channel<A>(k, qd[0], qd[1], qd[-1], qd[PP], qd[-PP], fc);
+      qd[0] = r;
       if (FORM == 1 && !MASK) {  // wall ghosts owned by this cell (channel-01.cpp:531-541)
-        if (i == 1) q[-1] = r;
-        if (i == nx) q[1] = 0.0;
-        if (j == 1) q[-PP] = r;
-        if (j == ny) q[PP] = r;
+        if (i == 1) qd[-1] = r;
+        if (i == nx) qd[1] = 0.0;
+        if (j == 1) qd[-PP] = r;
+        if (j == ny) qd[PP] = r;
       }
     }
   };
@@ -353,14 +375,18 @@ __global__ void __launch_bounds__(512, 1)
       pull_halo(-1);  // solid cells of the neighbours' boundary rows changed too
     }
     double a = 0.0;
-    for (int idx = tid; idx < nr * nx; idx += nth) {
-      const int l = 1 + idx / nx, i = 1 + idx - (l - 1) * nx, j = j0 + l;
-      if (MASK && !M[pm_idx(k, j, i)]) continue;
-      const double* q = P + size_t(l) * PP + i;
-      const double fc = F[size_t(l) * PP + i];
-      const double r = FORM == 0 ? res_cavity<A>(k, j, i, q[0], q[1], q[-1], q[PP], q[-PP], fc, k.idx2) : res_channel<A>(k, q[0], q[1], q[-1], q[PP], q[-PP], fc);
-      a = fmax(a, fabs(r));
-    }
+#pragma unroll
+    for (int colour = 0; colour < 2; ++colour)
+#pragma unroll
+      for (int q = 0; q < PM_CLUSTER_CPT; ++q) {
+        const int o = off[colour][q];
+        if (o < 0) continue;
+        const int j = ji[colour][q] >> 16, i = ji[colour][q] & 0xffff;
+        const double* qd = P + o;
+        const double r = FORM == 0 ? res_cavity<A>(k, j, i, qd[0], qd[1], qd[-1], qd[PP], qd[-PP], fv[colour][q], k.idx2)
+                                   : res_channel<A>(k, qd[0], qd[1], qd[-1], qd[PP], qd[-PP], fv[colour][q]);
+        a = fmax(a, fabs(r));
+      }
     const double m = block_max(a, red);
     if (tid == 0) slot[it & 1] = m;
     cluster.sync();
