@@ -757,6 +757,22 @@ static int lex_solve(pm_solver* s, int* iters_out, double* res_out) {
   if (k.case_id == PM_CASE_CAVITY) kern = reinterpret_cast<const void*>(&k_ppe_lex<0, false>);
   else if (k.has_mask) kern = reinterpret_cast<const void*>(&k_ppe_lex<1, true>);
   else kern = reinterpret_cast<const void*>(&k_ppe_lex<1, false>);
+  if (use_smem && k.nx <= 1024 && std::getenv("PM_LEX_GENERIC") == nullptr) {
+    // one column per thread: shuffled west value, register-carried south value, prefetched old operands
+    const void* kc;
+    if (k.case_id == PM_CASE_CAVITY) kc = reinterpret_cast<const void*>(&k_ppe_lex_cols<0, false>);
+    else if (k.has_mask) kc = reinterpret_cast<const void*>(&k_ppe_lex_cols<1, true>);
+    else kc = reinterpret_cast<const void*>(&k_ppe_lex_cols<1, false>);
+    CK(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const int thr = std::min(1024, std::max(256, ((k.nx + 31) / 32) * 32));
+    double* pgc = s->pl[s->p_cur];
+    const double* fcc = s->pl[PL_F];
+    const uint8_t* mc = s->mask;
+    PpeState* stc = s->d_state;
+    unsigned long long* rbc = s->d_res;
+    void* cargs[] = {(void*)&k, (void*)&pgc, (void*)&fcc, (void*)&mc, (void*)&stc, (void*)&rbc};
+    CK(cudaLaunchKernel(kc, dim3(1), dim3(thr), cargs, smem, s->stream));
+  } else {
   if (use_smem) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   double* pg = s->pl[s->p_cur];
   const double* f = s->pl[PL_F];
@@ -766,6 +782,7 @@ static int lex_solve(pm_solver* s, int* iters_out, double* res_out) {
   int us = use_smem;
   void* args[] = {(void*)&k, (void*)&pg, (void*)&f, (void*)&m, (void*)&st, (void*)&rb, (void*)&us};
   CK(cudaLaunchKernel(kern, dim3(1), dim3(threads), args, smem, s->stream));
+  }
   s->timing.kernel_launches++;
   s->timing.ppe_passes++;
   PMTRY(read_state(s));

@@ -109,6 +109,122 @@ __global__ void __launch_bounds__(1024, 1)
 }
 
 
+// Column-per-thread wavefront (nx <= 1024): the same order, with the dependent chain of one anti-diagonal
+// step cut down to what really depends on the previous step.  Thread t owns column i = t + 1 and walks it
+// upwards one cell per step (cell (i, d - i) at step d).  Of the five operands of a cell, only the NEW west
+// value (just produced by lane t-1) and the NEW south value (this thread's own previous result) are on the
+// critical path: west arrives by a warp shuffle (lane 0 of each warp and column 1 read shared memory), south
+// stays in a register, and the OLD centre / east / north values and f of the next step are prefetched before
+// the barrier.  Values and evaluation order are exactly those of the reference sweep.
+template <int FORM, bool MASK>
+__global__ void __launch_bounds__(1024, 1)
+    k_ppe_lex_cols(const __grid_constant__ KP k, double* pg, const double* __restrict__ f, const uint8_t* __restrict__ M,
+                   PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits) {
+  extern __shared__ double sp[];
+  __shared__ double red[32];
+  __shared__ double s_res;
+  const int nx = k.nx, ny = k.ny, PP = nx + 2;
+  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31;
+  for (int idx = tid; idx < (ny + 2) * PP; idx += nth) {
+    const int j = idx / PP, i = idx - j * PP;
+    sp[idx] = pg[pm_idx(k, j, i)];
+  }
+  double* P = sp;  // not restrict: neighbours write what this thread reads after each barrier
+  __syncthreads();
+
+  const int i = tid + 1;            // this thread's column (threads beyond nx only help outside the sweep)
+  const bool col = i <= nx;
+  const double tol = st->tol;
+  double res = st->res_init;
+  int it = 0;
+  while (res > tol && it < k.max_iters) {
+    ++it;
+    // operands of the first cell of the column (row 1), fetched before the wave reaches it
+    double pc = 0.0, pe = 0.0, pn = 0.0, fc = 0.0, mine = 0.0;  // mine: this thread's previous result (cell (i, j-1))
+    bool fl = true;
+    if (col) {
+      pc = P[PP + i]; pe = P[PP + i + 1]; pn = P[2 * PP + i];
+      fc = f[pm_idx(k, 1, i)];
+      if (MASK) fl = M[pm_idx(k, 1, i)] != 0;
+      mine = P[i];  // south ghost of row 1
+    }
+    for (int d = 2; d <= nx + ny; ++d) {
+      const int j = d - i;
+      const bool act = col && j >= 1 && j <= ny;
+      // west: lane-1 produced (i-1, j) in the previous step; warp-boundary lanes and column 1 read shared memory
+      double pw = __shfl_up_sync(0xffffffffu, mine, 1);
+      if (act && (lane == 0 || i == 1)) pw = P[j * PP + i - 1];
+      if (act) {
+        const double ps = mine;  // (i, j-1): own previous result, or the south ghost for j == 1
+        double nv = pc;
+        if (!MASK || fl) nv = FORM == 0 ? upd_cavity<Exact>(k, j, i, pc, pe, pw, pn, ps, fc) : upd_channel<Exact>(k, pc, pe, pw, pn, ps, fc);
+        P[j * PP + i] = nv;
+        mine = nv;  // a solid cell passes its unchanged value on
+        if (j + 1 <= ny) {  // operands of the next cell of the column: all still of the previous iterate
+          pc = pn;
+          pe = P[(j + 1) * PP + i + 1];
+          pn = P[(j + 2) * PP + i];
+          fc = f[pm_idx(k, j + 1, i)];
+          if (MASK) fl = M[pm_idx(k, j + 1, i)] != 0;
+        }
+      }
+      __syncthreads();
+    }
+    if (FORM == 1) {  // applyPressureGhosts, channel-01.cpp:531-541 / backwards_step-01.cpp:685-740
+      for (int t = 1 + tid; t <= max(nx, ny); t += nth) {
+        if (t <= ny) {
+          P[size_t(t) * PP] = P[size_t(t) * PP + 1];
+          P[size_t(t) * PP + nx + 1] = 0.0;
+        }
+        if (t <= nx) {
+          P[t] = P[size_t(PP) + t];
+          P[size_t(ny + 1) * PP + t] = P[size_t(ny) * PP + t];
+        }
+      }
+      __syncthreads();
+      if (MASK) {
+        for (int idx = tid; idx < nx * ny; idx += nth) {
+          const int j = 1 + idx / nx, ii = 1 + idx - (j - 1) * nx;
+          const size_t g = pm_idx(k, j, ii);
+          if (M[g]) continue;
+          double* c = P + size_t(j) * PP + ii;
+          double s = 0.0;
+          int n = 0;
+          if (ii > 1 && M[g - 1]) { s = __dadd_rn(s, c[-1]); ++n; }
+          if (ii < nx && M[g + 1]) { s = __dadd_rn(s, c[1]); ++n; }
+          if (j > 1 && M[g - k.pitch]) { s = __dadd_rn(s, c[-PP]); ++n; }
+          if (j < ny && M[g + k.pitch]) { s = __dadd_rn(s, c[PP]); ++n; }
+          if (n > 0) c[0] = __ddiv_rn(s, double(n));
+        }
+        __syncthreads();
+      }
+    }
+    double a = 0.0;
+    for (int idx = tid; idx < nx * ny; idx += nth) {
+      const int j = 1 + idx / nx, ii = 1 + idx - (j - 1) * nx;
+      const size_t g = pm_idx(k, j, ii);
+      if (MASK && !M[g]) continue;
+      const double* c = P + size_t(j) * PP + ii;
+      const double r = FORM == 0 ? res_cavity<Exact>(k, j, ii, c[0], c[1], c[-1], c[PP], c[-PP], f[g], k.idx2)
+                                 : res_channel<Exact>(k, c[0], c[1], c[-1], c[PP], c[-PP], f[g]);
+      a = fmax(a, fabs(r));
+    }
+    const double m = block_max(a, red);
+    if (tid == 0) s_res = m;
+    __syncthreads();
+    res = s_res;
+  }
+  for (int idx = tid; idx < (ny + 2) * PP; idx += nth) {
+    const int j = idx / PP, ii = idx - j * PP;
+    pg[pm_idx(k, j, ii)] = sp[idx];
+  }
+  if (tid == 0) {
+    st->iters = it;
+    st->done = 1;
+    if (it >= 1) res_bits[it] = (unsigned long long)__double_as_longlong(res);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Small grids (BASELINE configs[0..2]: <= 16 K cells, thousands of iterations per step): the same persistent
 // single-CTA solve for the Jacobi and red-black orderings.  The general path needs 3-5 launches per
