@@ -140,12 +140,18 @@ __global__ void __launch_bounds__(1024, 1)
   while (res > tol && it < k.max_iters) {
     ++it;
     // operands of the first cell of the column (row 1), fetched before the wave reaches it
-    double pc = 0.0, pe = 0.0, pn = 0.0, fc = 0.0, mine = 0.0;  // mine: this thread's previous result (cell (i, j-1))
-    bool fl = true;
+    double pc = 0.0, pe = 0.0, pn = 0.0, mine = 0.0;  // mine: this thread's previous result (cell (i, j-1))
+    // f (and the mask) come from global memory: a ring of the next four rows keeps their latency off the wave
+    double fr[4] = {0.0, 0.0, 0.0, 0.0};
+    bool mr[4] = {true, true, true, true};
     if (col) {
       pc = P[PP + i]; pe = P[PP + i + 1]; pn = P[2 * PP + i];
-      fc = f[pm_idx(k, 1, i)];
-      if (MASK) fl = M[pm_idx(k, 1, i)] != 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (1 + q <= ny) {
+          fr[q] = f[pm_idx(k, 1 + q, i)];
+          if (MASK) mr[q] = M[pm_idx(k, 1 + q, i)] != 0;
+        }
       mine = P[i];  // south ghost of row 1
     }
     for (int d = 2; d <= nx + ny; ++d) {
@@ -157,15 +163,19 @@ __global__ void __launch_bounds__(1024, 1)
       if (act) {
         const double ps = mine;  // (i, j-1): own previous result, or the south ghost for j == 1
         double nv = pc;
-        if (!MASK || fl) nv = FORM == 0 ? upd_cavity<Exact>(k, j, i, pc, pe, pw, pn, ps, fc) : upd_channel<Exact>(k, pc, pe, pw, pn, ps, fc);
+        if (!MASK || mr[0]) nv = FORM == 0 ? upd_cavity<Exact>(k, j, i, pc, pe, pw, pn, ps, fr[0]) : upd_channel<Exact>(k, pc, pe, pw, pn, ps, fr[0]);
         P[j * PP + i] = nv;
         mine = nv;  // a solid cell passes its unchanged value on
         if (j + 1 <= ny) {  // operands of the next cell of the column: all still of the previous iterate
           pc = pn;
           pe = P[(j + 1) * PP + i + 1];
           pn = P[(j + 2) * PP + i];
-          fc = f[pm_idx(k, j + 1, i)];
-          if (MASK) fl = M[pm_idx(k, j + 1, i)] != 0;
+        }
+        fr[0] = fr[1]; fr[1] = fr[2]; fr[2] = fr[3];
+        mr[0] = mr[1]; mr[1] = mr[2]; mr[2] = mr[3];
+        if (j + 4 <= ny) {
+          fr[3] = f[pm_idx(k, j + 4, i)];
+          if (MASK) mr[3] = M[pm_idx(k, j + 4, i)] != 0;
         }
       }
       __syncthreads();
