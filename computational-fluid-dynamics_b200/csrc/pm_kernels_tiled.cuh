@@ -140,10 +140,31 @@ struct Cells {
 };
 
 // m = max(m, |x|) where `on`, with the semantics of std::max(m, std::abs(x)) (a NaN never replaces m).
-// |x| is formed by masking the sign bit of the high word (one integer op, no FP64 issue slot).
+// fabs() folds into the compare and the select as an operand modifier: DSETP + FSEL + SEL per call.
 __device__ __forceinline__ void acc_max(double& m, double x, bool on) {
-  const double a = __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x));
-  if (on && a > m) m = a;
+  if (on && fabs(x) > m) m = fabs(x);
+}
+
+// Warp maximum of non-negative, non-NaN doubles (their bit patterns order like unsigned integers): two
+// REDUX.MAX over the high and the low word instead of five shuffle rounds of 64-bit compares.
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return __hiloint2double((int)mh, (int)ml);
+}
+
+// Production arithmetic, interior tiles: the residual in sum form.  FORM 0 takes the four-neighbour sum s,
+//   r = h^-2 * (s - 4 p) - f;  FORM 1 the two pair sums,  r = idx2*(pE+pW) + idy2*(pN+pS) - 2(idx2+idy2) p - f.
+// The same value as the reference's residual trees (cavity-01.cpp:670-673, channel-01.cpp:676-678) up to
+// rounding; the reference's own update tree sums the neighbours the same way (cavity-01.cpp:651-654).
+template <int FORM>
+__device__ __forceinline__ double res_sum4(const KP& k, double pc, double s, double f) {
+  static_assert(FORM == 0, "four-neighbour sum: isotropic form only");
+  return fma(k.idx2, fma(-4.0, pc, s), -f);
+}
+__device__ __forceinline__ double res_sum22(const KP& k, double pc, double sew, double sns, double f) {
+  return fma(-k.denom, pc, fma(k.idx2, sew, fma(k.idy2, sns, -f)));
 }
 
 // Shared-memory layout of the exchange tile ("split rows"): within each 128-double row the 64 even columns
@@ -233,6 +254,72 @@ __device__ __forceinline__ void rb_half(const KP& k, double* tpx, double* tpy, C
   }
   if (INT && !A::exact && POST) {
     const double m = fabs(k.om1) * post_raw;  // residual of the iterate just created: (1 - omega) * r
+    if (m > rmax_post) rmax_post = m;
+  }
+}
+
+// The same half-sweep for interior tiles with production arithmetic, written for a short instruction
+// stream: the relaxation in residual form, p += cw * r with r the residual (so the norm costs no extra
+// flops), neighbours summed instead of differenced, and -- in the isotropic (cavity) form -- the diagonal
+// pair sum p(r, .y) + p(r+1, .x) resp. p(r, .x) + p(r+1, .y) shared by the two same-colour cells of a row
+// pair that both have it as two of their four neighbours: 5.5 FP64 operations per cell and iterate.
+// A colour-1 cell's neighbours do not change during its half-sweep, so its residual after the update is
+// exactly (1 - omega) * r: POST takes max |r| before the update and scales it once.
+// The iterates differ from the reference trees by rounding only (exact_arith = 1 keeps the trees).
+template <int FORM, class C, int PX, bool PRE>
+__device__ __forceinline__ void rb_half_lean(const KP& k, double* tpx, double* tpy, Cells<C::RPT>& c, unsigned mOut,
+                                             double& rmax_pre, double& rmax_post) {
+  constexpr int SW = C::SW, RPT = C::RPT;
+  static_assert(RPT % 2 == 0, "rows are processed in pairs");
+  double mx = PRE ? rmax_pre : 0.0;
+#pragma unroll
+  for (int a = 0; a < RPT; a += 2) {
+    const int b = a + 1;
+    // row a: target tA (.x iff PX == 0); row b: the other column
+    double rA, rB;
+    if (PX == 0) {
+      const double wA = tpy[a * SW - 1];                                   // column 2q-1
+      const double sA = a >= 1 ? c.p0[a - 1] : tpx[(a - 1) * SW];
+      const double eB = tpx[b * SW + 1];                                   // column 2q+2
+      const double nB = b + 1 < RPT ? c.p1[b + 1] : tpy[(b + 1) * SW];
+      if (FORM == 0) {
+        const double d = c.p1[a] + c.p0[b];  // east + north of A == south + west of B
+        rA = res_sum4<0>(k, c.p0[a], d + (wA + sA), c.f0v(a));
+        rB = res_sum4<0>(k, c.p1[b], d + (eB + nB), c.f1v(b));
+      } else {
+        rA = res_sum22(k, c.p0[a], wA + c.p1[a], c.p0[b] + sA, c.f0v(a));
+        rB = res_sum22(k, c.p1[b], c.p0[b] + eB, nB + c.p1[a], c.f1v(b));
+      }
+      c.p0[a] = fma(k.cw, rA, c.p0[a]);
+      c.p1[b] = fma(k.cw, rB, c.p1[b]);
+      tpx[a * SW] = c.p0[a];
+      tpy[b * SW] = c.p1[b];
+      acc_max(mx, rA, (mOut >> a) & 1u);
+      acc_max(mx, rB, (mOut >> (16 + b)) & 1u);
+    } else {
+      const double eA = tpx[a * SW + 1];
+      const double sA = a >= 1 ? c.p1[a - 1] : tpy[(a - 1) * SW];
+      const double wB = tpy[b * SW - 1];
+      const double nB = b + 1 < RPT ? c.p0[b + 1] : tpx[(b + 1) * SW];
+      if (FORM == 0) {
+        const double d = c.p0[a] + c.p1[b];  // west + north of A == south + east of B
+        rA = res_sum4<0>(k, c.p1[a], d + (eA + sA), c.f1v(a));
+        rB = res_sum4<0>(k, c.p0[b], d + (wB + nB), c.f0v(b));
+      } else {
+        rA = res_sum22(k, c.p1[a], c.p0[a] + eA, c.p1[b] + sA, c.f1v(a));
+        rB = res_sum22(k, c.p0[b], wB + c.p1[b], nB + c.p0[a], c.f0v(b));
+      }
+      c.p1[a] = fma(k.cw, rA, c.p1[a]);
+      c.p0[b] = fma(k.cw, rB, c.p0[b]);
+      tpy[a * SW] = c.p1[a];
+      tpx[b * SW] = c.p0[b];
+      acc_max(mx, rA, (mOut >> (16 + a)) & 1u);
+      acc_max(mx, rB, (mOut >> b) & 1u);
+    }
+  }
+  if (PRE) rmax_pre = mx;
+  else {
+    const double m = fabs(k.om1) * mx;  // residual of the iterate just created
     if (m > rmax_post) rmax_post = m;
   }
 }
@@ -328,22 +415,29 @@ __device__ __forceinline__ void run_sweeps(const KP& k, double* tpx, double* tpy
     const bool commit = t < nsw;
     if (METHOD == PM_PPE_SOR_RB) {
       // colour 0 first ((i + j) even), as the oracle's red-black restatement
-      rb_half<A, FORM, INT, C, PAR0, true, false>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, commit, r_cur, r_next);
-      if (commit) {
+      if (INT && !A::exact) {  // interior tiles are only run with nsw > 0: commit is always true here
+        rb_half_lean<FORM, C, PAR0, true>(k, tpx, tpy, c, mOut, r_cur, r_next);
         __syncthreads();
-        rb_half<A, FORM, INT, C, 1 - PAR0, false, true>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, true, r_cur, r_next);
+        rb_half_lean<FORM, C, 1 - PAR0, false>(k, tpx, tpy, c, mOut, r_cur, r_next);
         __syncthreads();
+      } else {
+        rb_half<A, FORM, INT, C, PAR0, true, false>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, commit, r_cur, r_next);
+        if (commit) {
+          __syncthreads();
+          rb_half<A, FORM, INT, C, 1 - PAR0, false, true>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, true, r_cur, r_next);
+          __syncthreads();
+        }
       }
     } else {
       jacobi_sweep<A, FORM, INT, C>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, commit, r_cur);
     }
-    const double v = warp_max(r_cur);
+    const double v = warp_max_nonneg(r_cur);
     if (lane == 0 && v > 0.0) atomicMax(&red[t], (unsigned long long)__double_as_longlong(v));
     r_cur = r_next;
     r_next = 0.0;
   }
   // colour-1 part of the last iterate created (red-black); zero for Jacobi
-  const double v = warp_max(r_cur);
+  const double v = warp_max_nonneg(r_cur);
   if (lane == 0 && v > 0.0) atomicMax(&red[nloop], (unsigned long long)__double_as_longlong(v));
 }
 

@@ -186,6 +186,23 @@ def test_tiled_ppe_bit_exact(pm, orc, case_id, nx, ny, method, T, K):
     assert_fields_equal(S, O, (2,), "tiled ppe")
 
 
+@pytest.mark.parametrize("case_id,nx,ny,method,T", [(0, 400, 300, RB, 3), (0, 400, 300, RB, 2), (1, 384, 200, RB, 3), (0, 400, 300, JAC, 2),
+                                                   (1, 384, 200, JAC, 4)])
+def test_tiled_production_arithmetic_close_to_oracle(pm, orc, case_id, nx, ny, method, T):
+    """Production arithmetic on the tiled path, grids with interior tiles (the residual-form relaxation with
+    summed neighbours): iterate within 1e-12 of the oracle's relative to the field's scale, residual norm to
+    1e-9 relative, same iteration count."""
+    cfg = make_cfg(pm, case_id, nx, ny, method, 0, 23, 0.9 if method == JAC else None, path=2)
+    cfg.sweeps_per_pass = T
+    S, O = pm.Solver(cfg), orc.Oracle(cfg)
+    S.fill_random(29); O.fill_random(29)
+    rs, ro = S.ppe_solve(), O.ppe_solve()
+    assert (rs.iterations, rs.hit_cap) == (ro.iterations, ro.hit_cap)
+    assert abs(rs.residual - ro.residual) <= 1e-9 * ro.residual, (rs.residual, ro.residual)
+    a, b = S.download(2), O.field(2)
+    assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(b).max()), f"p off by {np.abs(a - b).max():.3e} vs scale {np.abs(b).max():.3e}"
+
+
 @pytest.mark.parametrize("case_id,nx,ny,T,steps", [(0, 40, 40, 2, 4), (0, 40, 40, 3, 4), (1, 93, 31, 2, 2), (1, 93, 31, 3, 2)])
 def test_tiled_stopping_rule_bit_exact(pm, orc, case_id, nx, ny, T, steps):
     """Run to the reference tolerance through the tiled path: the device-side loop test plus the
