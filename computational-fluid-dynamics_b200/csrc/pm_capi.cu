@@ -651,7 +651,7 @@ static int read_state(pm_solver* s) {
 
 
 // Tiled path: pass n reads buffer in0 ^ (n & 1) holding iterate n*T and writes iterate n*T + nsw to the
-// other buffer.  The loop test runs on the device (tiled_stop); the host only polls the sticky flag.
+// other buffer.  The loop test runs on the device (stop_words_eval); the host only polls the sticky flag.
 //
 // Slabs: the tile rows whose output the neighbours need (within H rows of the slab edge) are launched
 // first; their H halo rows travel by ncclSend/ncclRecv on the comm stream while the interior tile rows
@@ -1054,3 +1054,15 @@ extern "C" int pm_timer_stop(pm_solver* s, double* elapsed_ms) {
   *elapsed_ms = ms;
   return PM_OK;
 }
+
+#ifdef PM_TILE_PROFILE
+// Debug builds only (make variant EXTRA=-DPM_TILE_PROFILE): cycles per phase of the tiled kernel, summed over CTAs.
+extern "C" int pm_debug_tile_profile(unsigned long long out[8], int reset) {
+  if (out && cudaMemcpyFromSymbol(out, g_tile_prof, 8 * sizeof(unsigned long long)) != cudaSuccess) return PM_ERR_CUDA;
+  if (reset) {
+    unsigned long long z[8] = {};
+    if (cudaMemcpyToSymbol(g_tile_prof, z, sizeof z) != cudaSuccess) return PM_ERR_CUDA;
+  }
+  return PM_OK;
+}
+#endif

@@ -85,14 +85,42 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+#ifdef PM_TILE_PROFILE
+// Debug build only (make variant EXTRA=-DPM_TILE_PROFILE): cycles per phase summed over the CTAs, thread 0's clock.
+__device__ unsigned long long g_tile_prof[8];
+#define PM_PROF(slot) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_tile_prof[slot], (unsigned long long)(t_ - prof_t)); prof_t = t_; } } while (0)
+#else
+#define PM_PROF(slot) do { } while (0)
+#endif
+
 // Loop test of the reference for the pass that starts at iterate m0: has any iterate of the
-// previous pass (m0-T .. m0-1) met the tolerance?  Returns the first such iterate in *first.
-__device__ __forceinline__ bool tiled_stop(const PpeState* st, const unsigned long long* res_bits, int m0, int T, int* first) {
-  if (st->done) { *first = -1; return true; }
-  const int lo = max(1, m0 - T);
-  for (int m = lo; m < m0; ++m) {
-    const double r = __longlong_as_double((long long)res_bits[m]);
-    if (!(r > st->tol)) { *first = m; return true; }
+// previous pass (m0-T .. m0-1) met the tolerance?  The words it needs are fetched with T + 2
+// independent loads issued at kernel entry (one L2 round trip, overlapped with the tile loads) and
+// evaluated once the tile's own loads are in flight.
+template <int T>
+struct StopWords {
+  int done;
+  double tol;
+  unsigned long long res[T];
+};
+template <int T>
+__device__ __forceinline__ StopWords<T> stop_words_load(const PpeState* st, const unsigned long long* res_bits, int m0) {
+  StopWords<T> w;
+  w.done = st->done;
+  w.tol = st->tol;
+#pragma unroll
+  for (int q = 0; q < T; ++q) w.res[q] = res_bits[max(m0 - T + q, 0)];
+  return w;
+}
+// Returns true if the pass must not run; *first = the first iterate that met the tolerance (-1: decided by an earlier pass).
+template <int T>
+__device__ __forceinline__ bool stop_words_eval(const StopWords<T>& w, int m0, int* first) {
+  *first = -1;
+  if (w.done) return true;
+#pragma unroll
+  for (int q = 0; q < T; ++q) {
+    const int m = m0 - T + q;
+    if (m >= 1 && !(__longlong_as_double((long long)w.res[q]) > w.tol)) { *first = m; return true; }
   }
   return false;
 }
@@ -445,11 +473,15 @@ __device__ __forceinline__ void run_sweeps(const KP& k, double* tpx, double* tpy
 // split-row rewrite, the sweeps, the 128-bit write-out and the per-iterate residual atomics.
 template <class A, int FORM, int METHOD, int T, int PAR0>
 __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t* bar, uint32_t phase, unsigned long long* red,
-                                             double* __restrict__ pout, const double* __restrict__ f,
-                                             unsigned long long* __restrict__ res_bits, int m0, int nsw, int bx, int by) {
+                                             double* __restrict__ pout, const double* __restrict__ f, PpeState* __restrict__ st,
+                                             unsigned long long* __restrict__ res_bits, int m0, int nsw, int bx, int by,
+                                             const StopWords<T>& stopw, bool check_stop) {
   using C = TileCfg<METHOD, T>;
   constexpr int H = C::H, SW = C::SW, SH = C::SH, RPT = C::RPT, TX = C::TX, TY = C::TY;
   const int tid = threadIdx.x;
+#ifdef PM_TILE_PROFILE
+  long long prof_t = clock64();
+#endif
   const int x0 = 1 + bx * TX, y0 = 1 + by * TY;  // first output cell (i, jl)
   const int ib = x0 - H, jb = y0 - H;            // tile origin (i, jl)
   const int q = tid & 63, sg = tid >> 6;
@@ -507,7 +539,20 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
     }
   }
 #undef PM_PUT_F
+  PM_PROF(0);  // masks, f loads issued
+  if (check_stop) {  // the reference's loop test (uniform over the grid); the tile loads above are already in flight
+    int first;
+    if (stop_words_eval<T>(stopw, m0, &first)) {
+      if (first >= 0 && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+        st->iters = first;
+        st->done = 1;
+      }
+      mbar_wait(bar, phase);  // never leave with a bulk copy still landing in this CTA's shared memory
+      return;
+    }
+  }
   mbar_wait(bar, phase);
+  PM_PROF(1);  // wait for the TMA tile
   {  // TMA delivered natural row order: take the own cells, then rewrite the tile in the split-row layout
     const double* tn = tile + rr0 * SW + c0;
 #pragma unroll
@@ -527,10 +572,12 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
   }
   __syncthreads();
 
+  PM_PROF(2);  // own cells (this waits for the f registers too), split-row rewrite
   // the residual-only pass (nsw == 0) commits nothing and takes the general code path
   if (interior && nsw > 0) run_sweeps<A, FORM, METHOD, T, true, PAR0>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red);
   else run_sweeps<A, FORM, METHOD, T, false, PAR0>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red);
 
+  PM_PROF(3);  // the sweeps
   // ---- write the output block: 128-bit stores, plus the wall ghosts its cells own ----
   if (nsw > 0) {
     double* op = pout + pm_idx(k, jl0, i0);
@@ -562,6 +609,10 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
     const unsigned long long v = red[tid];
     if (v != 0ull && m >= 1 && m <= k.max_iters) atomicMax(&res_bits[m], v);
   }
+  PM_PROF(4);  // write-out, residual atomics
+#ifdef PM_TILE_PROFILE
+  if (tid == 0) atomicAdd(&g_tile_prof[7], 1ull);
+#endif
 }
 
 // One tile per CTA, two CTAs per SM: one CTA's loads overlap the other's sweeps.
@@ -578,27 +629,24 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
 
   const int tid = threadIdx.x;
   const int bx = blockIdx.x, by = blockIdx.y + tile_row0;
-  // The tile load goes out before anything else; the loop test of the reference (which needs three
-  // dependent global loads) is evaluated while the TMA is in flight.
+#ifdef PM_TILE_PROFILE
+  const long long prof_k = clock64();
+#endif
+  // The tile load goes out before anything else; the words of the reference's loop test follow as
+  // independent loads and are looked at only after the f loads of the tile have been issued.
   if (tid == 0) {
     mbar_init(&mbar, 1);
     fence_mbar_init();
     mbar_expect_tx(&mbar, C::SH * C::SW * 8);
     tma_load_2d(tile, &tmap_in, &mbar, PM_OFFC + 1 + bx * C::TX - C::H, k.padr + 1 + by * C::TY - C::H);
   }
+  StopWords<T> stopw;
+  if (!force) stopw = stop_words_load<T>(st, res_bits, m0);
   __syncthreads();
-  if (!force) {
-    int first = -1;
-    if (tiled_stop(st, res_bits, m0, T, &first)) {
-      if (first >= 0 && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
-        st->iters = first;
-        st->done = 1;
-      }
-      mbar_wait(&mbar, 0);  // never leave with a bulk copy still landing in this CTA's shared memory
-      return;
-    }
-  }
-  tile_process<A, FORM, METHOD, T, PAR0>(k, tile, &mbar, 0u, red, pout, f, res_bits, m0, nsw, bx, by);
+#ifdef PM_TILE_PROFILE
+  if (tid == 0) atomicAdd(&g_tile_prof[5], (unsigned long long)(clock64() - prof_k));
+#endif
+  tile_process<A, FORM, METHOD, T, PAR0>(k, tile, &mbar, 0u, red, pout, f, st, res_bits, m0, nsw, bx, by, stopw, !force);
 }
 
 // ---------------------------------------------------------------------------
