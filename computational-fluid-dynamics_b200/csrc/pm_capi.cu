@@ -686,9 +686,13 @@ static int tiled_pass(pm_solver* s, int in, int m0, int nsw, int force) {
       s->timing.kernel_launches++;
       if (nsw > 0) CK(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
     }
-    // entries m0 .. m0+max(nsw,1)-1 are now complete on this rank (both colour parts)
+  }
+  // entries m0 .. m0+max(nsw,1)-1 are now complete on this rank (both colour parts): slots -> res_bits
+  CK(tiled_fold_launch(&pl, k, s->d_res, m0, nsw, s->stream));
+  s->timing.kernel_launches++;
+  if (s->cfg.nranks > 1 && !force) {
     const int lo = std::max(m0, 1), hi = m0 + std::max(nsw, 1) - 1;
-    if (!force) PMTRY(allreduce_res(s, lo, hi - lo + 1));
+    PMTRY(allreduce_res(s, lo, hi - lo + 1));
   }
   s->timing.ppe_passes++;
   return PM_OK;
@@ -698,6 +702,7 @@ static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
   const TiledPlan& pl = s->tiled;
   const int K = s->cfg.max_iters, T = pl.sweeps;
   const int in0 = s->p_cur == PL_P0 ? 0 : 1;
+  CK(tiled_begin_solve(&pl, s->stream));
   if (s->cfg.nranks > 1) {  // halos of the inputs: f once per solve, p as deep as one pass reaches
     PMTRY(exchange_halo(s, s->pl[PL_F], pl.halo, s->stream));
     PMTRY(exchange_halo(s, pl.p[in0], pl.halo, s->stream));

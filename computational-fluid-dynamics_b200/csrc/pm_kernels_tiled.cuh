@@ -427,7 +427,8 @@ __device__ __forceinline__ void jacobi_sweep(const KP& k, double* tpx, double* t
 
 // All sweeps of one pass for one thread.  The sweep loop is NOT unrolled (the instruction footprint of
 // the hot path stays within the instruction cache); per-iterate residual maxima therefore go to shared
-// memory at the end of every sweep: warp shuffle tree, then one shared atomicMax per warp.
+// memory at the end of every sweep: two REDUX per warp, then a plain store into the warp's own slot
+// red[warp * (T + 1) + t] (a 64-bit shared atomicMax is a compare-and-swap loop).
 // PAR0 = colour of the .x cell of the thread's first row = (j0 & 1): i0 is always odd and TY, RPT are even,
 // so it is the same for every thread of every tile of a launch.
 template <class A, int FORM, int METHOD, int T, bool INT, int PAR0>
@@ -436,6 +437,7 @@ __device__ __forceinline__ void run_sweeps(const KP& k, double* tpx, double* tpy
                                            unsigned long long* __restrict__ red) {
   using C = TileCfg<METHOD, T>;
   const int lane = threadIdx.x & 31;
+  unsigned long long* redw = red + (threadIdx.x >> 5) * (T + 1);
   double r_cur = 0.0, r_next = 0.0;  // residual maxima of iterate m0+t and m0+t+1
   const int nloop = nsw > 0 ? nsw : 1;
 #pragma unroll 1
@@ -460,13 +462,32 @@ __device__ __forceinline__ void run_sweeps(const KP& k, double* tpx, double* tpy
       jacobi_sweep<A, FORM, INT, C>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, commit, r_cur);
     }
     const double v = warp_max_nonneg(r_cur);
-    if (lane == 0 && v > 0.0) atomicMax(&red[t], (unsigned long long)__double_as_longlong(v));
+    if (lane == 0) redw[t] = (unsigned long long)__double_as_longlong(v);
     r_cur = r_next;
     r_next = 0.0;
   }
   // colour-1 part of the last iterate created (red-black); zero for Jacobi
   const double v = warp_max_nonneg(r_cur);
-  if (lane == 0 && v > 0.0) atomicMax(&red[nloop], (unsigned long long)__double_as_longlong(v));
+  if (lane == 0) redw[nloop] = (unsigned long long)__double_as_longlong(v);
+}
+
+// Where the residual maxima of a pass are collected (see the end of tile_process): PM_FOLD_SLOTS lines of 16
+// words, a ring of per-iterate maxima per slot; slot = linear CTA index % slots.
+#define PM_FOLD_SLOTS 32
+// One warp, launched behind the launches of a pass: res_bits[m] = max(res_bits[m], max over slots) for the
+// iterates lo..hi the pass has completed; their ring entries are cleared for reuse.
+__global__ void k_tiled_fold(unsigned long long* __restrict__ part, unsigned long long* __restrict__ res_bits, int lo, int hi) {
+  static_assert(PM_FOLD_SLOTS == 32, "one lane per slot");
+  const int lane = threadIdx.x;
+  for (int m = lo; m <= hi; ++m) {
+    unsigned long long* e = part + size_t(lane) * 16 + (m & 7);
+    const unsigned long long v = *e;
+    *e = 0ull;
+    const unsigned hi32 = unsigned(v >> 32), mh = __reduce_max_sync(0xffffffffu, hi32);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi32 == mh ? unsigned(v) : 0u);
+    const unsigned long long vm = (unsigned long long)mh << 32 | ml;
+    if (lane == 0 && vm > res_bits[m]) res_bits[m] = vm;
+  }
 }
 
 // Everything one CTA does for one tile once its TMA load has been issued on `bar`: masks, f loads, wait,
@@ -474,7 +495,7 @@ __device__ __forceinline__ void run_sweeps(const KP& k, double* tpx, double* tpy
 template <class A, int FORM, int METHOD, int T, int PAR0>
 __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t* bar, uint32_t phase, unsigned long long* red,
                                              double* __restrict__ pout, const double* __restrict__ f, PpeState* __restrict__ st,
-                                             unsigned long long* __restrict__ res_bits, int m0, int nsw, int bx, int by,
+                                             unsigned long long* __restrict__ res_bits, unsigned long long* __restrict__ fold_part, int m0, int nsw, int bx, int by,
                                              const StopWords<T>& stopw, bool check_stop) {
   using C = TileCfg<METHOD, T>;
   constexpr int H = C::H, SW = C::SW, SH = C::SH, RPT = C::RPT, TX = C::TX, TY = C::TY;
@@ -507,7 +528,7 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
   // Every updatable cell of the tile strictly inside the domain (uniform over the block)?
   const bool interior = ib + 1 >= 2 && ib + SW - 2 <= k.nx - 1 && k.j0 + jb + 1 >= 2 && k.j0 + jb + SH - 2 <= k.ny - 1 &&
                         jb + SH - 1 <= k.nyl + H;
-  if (tid <= T) red[tid] = 0ull;  // ordered before the first shared atomic by the barriers below
+  if (tid < (PM_TILE_THREADS / 32) * (T + 1)) red[tid] = 0ull;  // ordered before the warps' stores by the barriers below
 
   // f: HBM -> registers (or the thread's private shared-memory slots), 128-bit row loads, overlapping the TMA transfer of p
   Cells<RPT> c;
@@ -600,14 +621,21 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
     }
   }
 
-  // ---- residual norms: one global atomic per iterate and tile ----
+  // ---- residual norms ----
+  // Per iterate and tile one global atomicMax, spread over PM_FOLD_SLOTS cache lines (a single line would take
+  // (T+1) * tiles atomics per pass and stall every load that touches it); k_tiled_fold, launched behind the pass,
+  // folds the slots into res_bits[m] for the iterates the pass completes.  Ring index m & 7: at most T + 1 <= 5
+  // iterates are open at a time.
   __syncthreads();  // also: nobody touches the tile in shared memory after this point
   if (tid <= T) {
     const int m = m0 + tid;
-    // Jacobi: red[t] is the full residual of iterate m0+t.  Red-black: red[t] collects the colour-0 part of
+    // Jacobi: entry t is the full residual of iterate m0+t.  Red-black: entry t collects the colour-0 part of
     // iterate m0+t (before sweep t+1 replaces it) and the colour-1 part taken right after sweep t created it.
-    const unsigned long long v = red[tid];
-    if (v != 0ull && m >= 1 && m <= k.max_iters) atomicMax(&res_bits[m], v);
+    unsigned long long v = 0ull;
+#pragma unroll
+    for (int w = 0; w < PM_TILE_THREADS / 32; ++w) v = max(v, red[w * (T + 1) + tid]);
+    unsigned long long* mine = fold_part + size_t((blockIdx.y * gridDim.x + blockIdx.x) & (PM_FOLD_SLOTS - 1)) * 16;
+    if (v != 0ull && m >= 1 && m <= k.max_iters) atomicMax(&mine[m & 7], v);
   }
   PM_PROF(4);  // write-out, residual atomics
 #ifdef PM_TILE_PROFILE
@@ -619,16 +647,18 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
 template <class A, int FORM, int METHOD, int T, int PAR0>
 __global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
     k_ppe_tiled(const __grid_constant__ KP k, const __grid_constant__ CUtensorMap tmap_in, double* __restrict__ pout,
-                const double* __restrict__ f, PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits, int m0,
-                int nsw, int force, int tile_row0) {
+                const double* __restrict__ f, PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits,
+                unsigned long long* __restrict__ fold_part, int m0, int nsw, int force, int tile_row0) {
   using C = TileCfg<METHOD, T>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   double* tile = reinterpret_cast<double*>(smem_raw) + C::SW;  // one spare row above (and one below)
   __shared__ __align__(8) uint64_t mbar;
-  __shared__ unsigned long long red[T + 1];  // bit patterns of the residual maxima of iterates m0 .. m0+T
+  __shared__ unsigned long long red[(PM_TILE_THREADS / 32) * (T + 1)];  // per warp: bit patterns of the residual maxima of iterates m0 .. m0+T
 
   const int tid = threadIdx.x;
-  const int bx = blockIdx.x, by = blockIdx.y + tile_row0;
+  // tile rows rotated by one: the last row of the launch (all boundary tiles at the top wall, several times
+  // slower than interior tiles) starts in the first wave instead of forming the tail
+  const int bx = blockIdx.x, by = tile_row0 + (blockIdx.y == 0 ? int(gridDim.y) - 1 : int(blockIdx.y) - 1);
 #ifdef PM_TILE_PROFILE
   const long long prof_k = clock64();
 #endif
@@ -646,7 +676,7 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
 #ifdef PM_TILE_PROFILE
   if (tid == 0) atomicAdd(&g_tile_prof[5], (unsigned long long)(clock64() - prof_k));
 #endif
-  tile_process<A, FORM, METHOD, T, PAR0>(k, tile, &mbar, 0u, red, pout, f, st, res_bits, m0, nsw, bx, by, stopw, !force);
+  tile_process<A, FORM, METHOD, T, PAR0>(k, tile, &mbar, 0u, red, pout, f, st, res_bits, fold_part, m0, nsw, bx, by, stopw, !force);
 }
 
 // ---------------------------------------------------------------------------
@@ -661,6 +691,8 @@ struct TiledPlan {
   CUtensorMap map[2];   // p ping / p pong
   double* p[2] = {nullptr, nullptr};
   const void* kernel = nullptr;
+  unsigned long long* fold_part = nullptr;  // PM_FOLD_SLOTS * 16 words
+  size_t fold_bytes = 0;
 };
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -732,15 +764,32 @@ static inline bool tiled_create(TiledPlan* pl, const pm_config& c, const KP& k, 
   }
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes);
   if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return false; }
+  pl->fold_bytes = size_t(PM_FOLD_SLOTS) * 16 * sizeof(unsigned long long);
+  e = cudaMalloc(&pl->fold_part, pl->fold_bytes);
+  if (e != cudaSuccess) { *err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return false; }
   return true;
 }
-static inline void tiled_destroy(TiledPlan*) {}
+static inline void tiled_destroy(TiledPlan* pl) {
+  if (pl->fold_part) cudaFree(pl->fold_part);
+  pl->fold_part = nullptr;
+}
+// Before the first pass of a solve (stream order): empty slots.
+static inline cudaError_t tiled_begin_solve(const TiledPlan* pl, cudaStream_t stream) {
+  return cudaMemsetAsync(pl->fold_part, 0, pl->fold_bytes, stream);
+}
 
 // Launch one pass: reads iterate m0 from buffer `in`, writes iterate m0+nsw to the other buffer.
 static inline cudaError_t tiled_launch(const TiledPlan* pl, const KP& k, int in, const double* f, PpeState* st, unsigned long long* res,
                                        int m0, int nsw, int force, int tile_row0, int tile_rows, cudaStream_t stream) {
   double* pout = pl->p[in ^ 1];
-  void* args[] = {(void*)&k, (void*)&pl->map[in], (void*)&pout, (void*)&f, (void*)&st, (void*)&res,
+  void* args[] = {(void*)&k, (void*)&pl->map[in], (void*)&pout, (void*)&f, (void*)&st, (void*)&res, (void*)&pl->fold_part,
                   (void*)&m0, (void*)&nsw, (void*)&force, (void*)&tile_row0};
   return cudaLaunchKernel(pl->kernel, dim3(pl->tiles_x, tile_rows), dim3(PM_TILE_THREADS), args, size_t(pl->smem_bytes), stream);
+}
+// Behind all launches of the pass that started at iterate m0 with nsw sweeps.
+static inline cudaError_t tiled_fold_launch(const TiledPlan* pl, const KP& k, unsigned long long* res, int m0, int nsw, cudaStream_t stream) {
+  const int lo = std::max(m0, 1), hi = std::min(m0 + std::max(nsw, 1) - 1, k.max_iters);
+  if (hi < lo) return cudaSuccess;
+  k_tiled_fold<<<1, 32, 0, stream>>>(pl->fold_part, res, lo, hi);
+  return cudaGetLastError();
 }
