@@ -25,6 +25,20 @@
 // ---------------------------------------------------------------------------
 enum { PL_U = 0, PL_V, PL_US, PL_VS, PL_F, PL_P0, PL_P1, PL_COUNT };
 
+// Streamed host-resident steps (pm_host_step_*): three rotating (u, v) plane sets, a pressure out-plane,
+// one stream per copy direction.
+struct HostPipe {
+  bool ready = false;
+  double* extra = nullptr;  // 5 planes: u[1], u[2], v[1], v[2], pout
+  double* u[3] = {}, *v[3] = {};
+  double* pout = nullptr;
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t ev_up[3] = {}, ev_down[3] = {}, ev_step = nullptr, ev_pdown = nullptr;
+  bool down_pending[3] = {false, false, false}, pdown_pending = false;
+  long long submitted = 0, run = 0;
+  struct Job { double* u_out; double* v_out; double* p_out; } job[3] = {};
+};
+
 struct pm_solver {
   pm_config cfg{};
   KP kp{};
@@ -52,6 +66,7 @@ struct pm_solver {
   TiledPlan tiled{};
   PmNccl nccl{};
   pm_timing timing{};
+  HostPipe hp{};
   std::string err;
 };
 
@@ -194,6 +209,18 @@ static int destroy_impl(pm_solver* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   pm_nccl_destroy(&s->nccl);
   tiled_destroy(&s->tiled);
+  if (s->hp.ready) {
+    cudaStreamSynchronize(s->hp.h2d);
+    cudaStreamSynchronize(s->hp.d2h);
+    s->pl[PL_U] = s->hp.u[0];  // planes of s->base
+    s->pl[PL_V] = s->hp.v[0];
+    for (int q = 0; q < 3; ++q) { cudaEventDestroy(s->hp.ev_up[q]); cudaEventDestroy(s->hp.ev_down[q]); }
+    cudaEventDestroy(s->hp.ev_step);
+    cudaEventDestroy(s->hp.ev_pdown);
+    cudaStreamDestroy(s->hp.h2d);
+    cudaStreamDestroy(s->hp.d2h);
+    cudaFree(s->hp.extra);
+  }
   if (s->base) cudaFree(s->base);
   if (s->mask) cudaFree(s->mask);
   if (s->d_state) cudaFree(s->d_state);
@@ -436,6 +463,10 @@ extern "C" int pm_fill_zero(pm_solver* s) {
   if (!s) return PM_ERR_INVALID_ARGUMENT;
   CK(cudaSetDevice(s->device));
   CK(cudaMemsetAsync(s->base, 0, s->plane * PL_COUNT * sizeof(double), s->stream));
+  if (s->hp.ready) {  // u, v may currently live in one of the streaming plane sets
+    PMTRY(pm_host_step_drain(s));
+    CK(cudaMemsetAsync(s->hp.extra, 0, s->plane * 5 * sizeof(double), s->stream));
+  }
   s->p_cur = PL_P0;
   s->f_max_valid = false;
   return PM_OK;
@@ -1009,6 +1040,109 @@ extern "C" int pm_step(pm_solver* s, int nsteps, pm_ppe_result* last) {
     }
   }
   if (last) *last = r;
+  return PM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host-resident steps, streamed
+// ---------------------------------------------------------------------------
+static int host_pipe_init(pm_solver* s) {
+  HostPipe& h = s->hp;
+  if (h.ready) return PM_OK;
+  CK(cudaMalloc(&h.extra, s->plane * 5 * sizeof(double)));
+  CK(cudaMemsetAsync(h.extra, 0, s->plane * 5 * sizeof(double), s->stream));  // pad cells of every plane are zero
+  h.u[0] = s->pl[PL_U]; h.v[0] = s->pl[PL_V];
+  h.u[1] = h.extra; h.u[2] = h.extra + s->plane;
+  h.v[1] = h.extra + 2 * s->plane; h.v[2] = h.extra + 3 * s->plane;
+  h.pout = h.extra + 4 * s->plane;
+  CK(cudaStreamCreateWithFlags(&h.h2d, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h.d2h, cudaStreamNonBlocking));
+  for (int q = 0; q < 3; ++q) {
+    CK(cudaEventCreateWithFlags(&h.ev_up[q], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h.ev_down[q], cudaEventDisableTiming));
+  }
+  CK(cudaEventCreateWithFlags(&h.ev_step, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h.ev_pdown, cudaEventDisableTiming));
+  CK(cudaStreamSynchronize(s->stream));
+  h.ready = true;
+  return PM_OK;
+}
+// This rank's rows of `field` between a dense host array (pm_upload_slab layout) and `plane`, asynchronously.
+static int slab_copy_async(pm_solver* s, int field, double* plane, double* host, size_t count, bool to_device, cudaStream_t st) {
+  int rows, cols, ja, jb;
+  field_dims(s, field, &rows, &cols);
+  local_row_span(s, rows, true, &ja, &jb);
+  const size_t n = size_t(jb - ja + 1);
+  if (count != n * cols) return fail(s, PM_ERR_INVALID_ARGUMENT, "slab of field %d expects %zu elements, got %zu", field, n * cols, count);
+  const KP& k = s->kp;
+  if (to_device)
+    CK(cudaMemcpy2DAsync(plane + pm_idx(k, ja, 0), size_t(k.pitch) * 8, host, size_t(cols) * 8, size_t(cols) * 8, n, cudaMemcpyHostToDevice, st));
+  else
+    CK(cudaMemcpy2DAsync(host, size_t(cols) * 8, plane + pm_idx(k, ja, 0), size_t(k.pitch) * 8, size_t(cols) * 8, n, cudaMemcpyDeviceToHost, st));
+  return PM_OK;
+}
+
+extern "C" int pm_host_step_submit(pm_solver* s, const double* u_in, size_t u_count, const double* v_in, size_t v_count,
+                                   double* u_out, double* v_out, double* p_out, size_t p_count) {
+  if (!s || !u_in || !v_in || !u_out || !v_out || !p_out) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  PMTRY(host_pipe_init(s));
+  HostPipe& h = s->hp;
+  if (h.submitted - h.run >= 2) return fail(s, PM_ERR_INVALID_ARGUMENT, "two steps are already submitted and not yet run");
+  {
+    int rows, cols, ja, jb;
+    field_dims(s, PM_FIELD_P, &rows, &cols);
+    local_row_span(s, rows, true, &ja, &jb);
+    if (p_count != size_t(jb - ja + 1) * cols) return fail(s, PM_ERR_INVALID_ARGUMENT, "p slab expects %zu elements, got %zu", size_t(jb - ja + 1) * cols, p_count);
+  }
+  const int set = int(h.submitted % 3);
+  // the planes of this set may still be the source of the download of the step three back
+  if (h.down_pending[set]) CK(cudaStreamWaitEvent(h.h2d, h.ev_down[set], 0));
+  PMTRY(slab_copy_async(s, PM_FIELD_U, h.u[set], const_cast<double*>(u_in), u_count, true, h.h2d));
+  PMTRY(slab_copy_async(s, PM_FIELD_V, h.v[set], const_cast<double*>(v_in), v_count, true, h.h2d));
+  CK(cudaEventRecord(h.ev_up[set], h.h2d));
+  h.job[set] = {u_out, v_out, p_out};
+  h.submitted++;
+  return PM_OK;
+}
+
+extern "C" int pm_host_step_run(pm_solver* s, pm_ppe_result* r) {
+  if (!s) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  HostPipe& h = s->hp;
+  if (!h.ready || h.run >= h.submitted) return fail(s, PM_ERR_INVALID_ARGUMENT, "no submitted step to run");
+  const int set = int(h.run % 3);
+  CK(cudaStreamWaitEvent(s->stream, h.ev_up[set], 0));
+  s->pl[PL_U] = h.u[set];
+  s->pl[PL_V] = h.v[set];
+  PMTRY(pm_step(s, 1, r));
+  // results: p leaves through its own plane (the next solve overwrites both pressure buffers); u, v stay where
+  // they are -- the next two steps use the other plane sets
+  if (h.pdown_pending) CK(cudaStreamWaitEvent(s->stream, h.ev_pdown, 0));
+  CK(cudaMemcpyAsync(h.pout, s->pl[s->p_cur], s->plane * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+  CK(cudaEventRecord(h.ev_step, s->stream));
+  CK(cudaStreamWaitEvent(h.d2h, h.ev_step, 0));
+  const HostPipe::Job& j = h.job[set];
+  int rows, cols, ja, jb;
+  auto count_of = [&](int field) { field_dims(s, field, &rows, &cols); local_row_span(s, rows, true, &ja, &jb); return size_t(jb - ja + 1) * cols; };
+  PMTRY(slab_copy_async(s, PM_FIELD_P, h.pout, j.p_out, count_of(PM_FIELD_P), false, h.d2h));
+  CK(cudaEventRecord(h.ev_pdown, h.d2h));
+  h.pdown_pending = true;
+  PMTRY(slab_copy_async(s, PM_FIELD_U, h.u[set], j.u_out, count_of(PM_FIELD_U), false, h.d2h));
+  PMTRY(slab_copy_async(s, PM_FIELD_V, h.v[set], j.v_out, count_of(PM_FIELD_V), false, h.d2h));
+  CK(cudaEventRecord(h.ev_down[set], h.d2h));
+  h.down_pending[set] = true;
+  h.run++;
+  return PM_OK;
+}
+
+extern "C" int pm_host_step_drain(pm_solver* s) {
+  if (!s) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  if (!s->hp.ready) return PM_OK;
+  CK(cudaStreamSynchronize(s->hp.h2d));
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaStreamSynchronize(s->hp.d2h));
   return PM_OK;
 }
 

@@ -62,7 +62,7 @@ EXPORTS = [
     "pm_config_init", "pm_slab_range", "pm_create", "pm_destroy", "pm_last_error", "pm_status_string",
     "pm_abi_version", "pm_nccl_unique_id", "pm_upload", "pm_download", "pm_slab_rows", "pm_upload_slab", "pm_download_slab", "pm_upload_mask", "pm_download_mask",
     "pm_fill_random", "pm_fill_random_scaled", "pm_fill_zero", "pm_apply_bc", "pm_predict", "pm_source", "pm_ppe_solve", "pm_correct",
-    "pm_step", "pm_diagnostics", "pm_sync", "pm_get_timing", "pm_timer_start", "pm_timer_stop",
+    "pm_step", "pm_host_step_submit", "pm_host_step_run", "pm_host_step_drain", "pm_diagnostics", "pm_sync", "pm_get_timing", "pm_timer_start", "pm_timer_stop",
 ]
 
 _lib = None
@@ -101,6 +101,9 @@ def lib():
         getattr(L, n).argtypes = [vp]
     L.pm_ppe_solve.argtypes = [vp, C.POINTER(PmPpeResult)]
     L.pm_step.argtypes = [vp, C.c_int, C.POINTER(PmPpeResult)]
+    L.pm_host_step_submit.argtypes = [vp, dp, C.c_size_t, dp, C.c_size_t, dp, dp, dp, C.c_size_t]
+    L.pm_host_step_run.argtypes = [vp, C.POINTER(PmPpeResult)]
+    L.pm_host_step_drain.argtypes = [vp]
     L.pm_diagnostics.argtypes = [vp, dp, dp]
     L.pm_get_timing.argtypes = [vp, C.POINTER(PmTiming)]
     L.pm_timer_start.argtypes = [vp]
@@ -215,6 +218,20 @@ class Solver:
 
     def download_slab_ptr(self, field, ptr, count):
         self._ck(lib().pm_download_slab(self._h, field, C.cast(ptr, C.POINTER(C.c_double)), count))
+
+    def host_step_submit(self, u_in, v_in, u_out, v_out, p_out):
+        """(ptr, count) pairs for the inputs; ptrs for the outputs, p with its count (see pm_host_step_submit)."""
+        dp = C.POINTER(C.c_double)
+        self._ck(lib().pm_host_step_submit(self._h, C.cast(u_in[0], dp), u_in[1], C.cast(v_in[0], dp), v_in[1],
+                                           C.cast(u_out, dp), C.cast(v_out, dp), C.cast(p_out[0], dp), p_out[1]))
+
+    def host_step_run(self):
+        r = PmPpeResult()
+        self._ck(lib().pm_host_step_run(self._h, C.byref(r)))
+        return r
+
+    def host_step_drain(self):
+        self._ck(lib().pm_host_step_drain(self._h))
 
     def timer_start(self):
         self._ck(lib().pm_timer_start(self._h))

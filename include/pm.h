@@ -168,6 +168,22 @@ int pm_correct(pm_solver* s);                      /* applyPressureCorrection */
  * (cavity-01.cpp:387-390 / channel-01.cpp:368-375).  *last may be NULL. */
 int pm_step(pm_solver* s, int nsteps, pm_ppe_result* last);
 
+/* ---- host-resident steps, streamed ---------------------------------------
+ * One projection step per call on inputs and results that live in HOST memory (pinned for full PCIe speed):
+ * this rank's slab rows of u and v in, of u, v and p out, in the layout of pm_upload_slab / pm_download_slab.
+ *   pm_host_step_submit  enqueues the upload of (u, v) for one step and records where its results go;
+ *   pm_host_step_run     runs the oldest submitted step -- pm_step(1) on the uploaded velocities; the pressure
+ *                        state stays on the device from step to step, as in the reference's time loop -- and
+ *                        enqueues the download of (u, v, p); returns when the pressure solve has finished;
+ *   pm_host_step_drain   blocks until every enqueued download has landed in host memory.
+ * Copies run on their own streams through three rotating (u, v) plane sets, so the upload of step n+1 and the
+ * download of step n-1 overlap the kernels of step n.  At most two steps may be submitted and not yet run.
+ * The host buffers of a step must stay valid and untouched until pm_host_step_drain returns. */
+int pm_host_step_submit(pm_solver* s, const double* u_in, size_t u_count, const double* v_in, size_t v_count,
+                        double* u_out, double* v_out, double* p_out, size_t p_count);
+int pm_host_step_run(pm_solver* s, pm_ppe_result* r);
+int pm_host_step_drain(pm_solver* s);
+
 /* max|div u| over (fluid) cells and mean kinetic energy of the cell-centred
  * velocity (logStatistics, cavity-01.cpp:741-766). */
 int pm_diagnostics(pm_solver* s, double* max_div, double* avg_ke);

@@ -95,6 +95,42 @@ def test_every_phase_bit_exact(pm, orc, case_id, nx, ny, method, omega):
     assert abs(ds[1] - do[1]) <= 1e-12 * max(1.0, abs(do[1]))
 
 
+@pytest.mark.parametrize("case_id,nx,ny,method", [(0, 96, 80, RB), (1, 93, 31, RB), (2, 64, 16, RB), (0, 300, 200, JAC)])
+def test_streamed_host_steps_equal_plain_steps(pm, case_id, nx, ny, method):
+    """pm_host_step_submit/run/drain (uploads, kernels and downloads of neighbouring steps overlapped through
+    rotating plane sets) must return exactly what upload -> pm_step -> download returns, step by step."""
+    rng = np.random.default_rng(5)
+    cfg = make_cfg(pm, case_id, nx, ny, method, 1, 40, 0.9 if method == JAC else None, path=0)
+    nsteps = 5
+    ins = [(rng.uniform(-1, 1, pm.field_shape(0, nx, ny)), rng.uniform(-1, 1, pm.field_shape(1, nx, ny))) for _ in range(nsteps)]
+    A = pm.Solver(cfg)
+    want = []
+    for u, v in ins:
+        A.upload(0, u); A.upload(1, v)
+        r = A.step(1)
+        want.append((r.iterations, r.residual, A.download(0), A.download(1), A.download(2)))
+    A.close()
+    B = pm.Solver(cfg)
+    outs = [tuple(np.full(pm.field_shape(f, nx, ny), np.nan) for f in (0, 1, 2)) for _ in range(nsteps)]
+    res = []
+    def submit(n):
+        (u, v), (uo, vo, po) = ins[n], outs[n]
+        B.host_step_submit((u.ctypes.data, u.size), (v.ctypes.data, v.size), uo.ctypes.data, vo.ctypes.data, (po.ctypes.data, po.size))
+    submit(0)
+    for n in range(nsteps):
+        if n + 1 < nsteps:
+            submit(n + 1)
+        res.append(B.host_step_run())
+    B.host_step_drain()
+    for n in range(nsteps):
+        assert (res[n].iterations, res[n].residual) == want[n][:2], f"step {n}"
+        for q in range(3):
+            assert bits_equal(outs[n][q], want[n][2 + q]), f"step {n} field {q}"
+    # the handle's own state is that of the last step
+    assert bits_equal(B.download(0), want[-1][2]) and bits_equal(B.download(2), want[-1][4])
+    B.close()
+
+
 @pytest.mark.parametrize("case_id,nx,ny", CASES)
 def test_production_arithmetic_close_to_oracle(pm, orc, case_id, nx, ny):
     """exact_arith=0 (FMA contraction, reciprocal multiply, tree-summed mean): 1e-12 relative after one step."""
