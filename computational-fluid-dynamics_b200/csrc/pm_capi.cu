@@ -98,6 +98,13 @@ static int fail(pm_solver* s, int status, const char* fmt, ...) {
     if (st_ != PM_OK) return st_; \
   } while (0)
 
+// `bytes` (a multiple of 8) from device memory to device-addressable memory, in stream order, without a copy engine.
+static int publish_words(pm_solver* s, void* dst, const void* src, size_t bytes) {
+  k_publish_words<<<1, 32, 0, s->stream>>>(static_cast<const unsigned long long*>(src), static_cast<unsigned long long*>(dst), int(bytes / 8));
+  CKL(s);
+  return PM_OK;
+}
+
 static inline dim3 cell_block() { return dim3(PM_BX, PM_BY); }
 static inline dim3 cell_grid(const KP& k) { return dim3((k.nx + PM_BX - 1) / PM_BX, (k.nyl + PM_BY - 1) / PM_BY); }
 static inline dim3 half_grid(const KP& k) { return dim3(((k.nx + 1) / 2 + PM_BX - 1) / PM_BX, (k.nyl + PM_BY - 1) / PM_BY); }
@@ -573,7 +580,7 @@ extern "C" int pm_source(pm_solver* s) {
   CKL(s);
   if (cav) {
     // the tolerance rule reads max|f| of this very pass (cavity-01.cpp:628-632)
-    CK(cudaMemcpyAsync(&s->d_state->maxf2_bits, &s->d_state->maxf_bits, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s->stream));
+    PMTRY(publish_words(s, &s->d_state->maxf2_bits, &s->d_state->maxf_bits, sizeof(unsigned long long)));
     s->f_max_valid = true;
     return PM_OK;
   }
@@ -675,7 +682,8 @@ static int launch_iteration_simple(pm_solver* s, int krel, int kabs) {
 }
 
 static int read_state(pm_solver* s) {
-  CK(cudaMemcpyAsync(s->h_state, s->d_state, sizeof(PpeState), cudaMemcpyDeviceToHost, s->stream));
+  static_assert(sizeof(PpeState) % 8 == 0, "PpeState is copied in 64-bit words");
+  PMTRY(publish_words(s, s->h_state, s->d_state, sizeof(PpeState)));
   CK(cudaStreamSynchronize(s->stream));
   return PM_OK;
 }
@@ -772,7 +780,7 @@ static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
   }
   s->p_cur = buf ? PL_P1 : PL_P0;
   if (iters >= 1) {
-    CK(cudaMemcpyAsync(s->h_res, s->d_res + iters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    PMTRY(publish_words(s, s->h_res, s->d_res + iters, sizeof(unsigned long long)));
     CK(cudaStreamSynchronize(s->stream));
     std::memcpy(res_out, s->h_res, 8);
   } else {
@@ -824,7 +832,7 @@ static int lex_solve(pm_solver* s, int* iters_out, double* res_out) {
   PMTRY(read_state(s));
   const int iters = s->h_state->iters;
   if (iters >= 1) {
-    CK(cudaMemcpyAsync(s->h_res, s->d_res + iters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    PMTRY(publish_words(s, s->h_res, s->d_res + iters, sizeof(unsigned long long)));
     CK(cudaStreamSynchronize(s->stream));
     std::memcpy(res_out, s->h_res, 8);
   } else {
@@ -894,7 +902,7 @@ static int small_solve(pm_solver* s, int* iters_out, double* res_out) {
       PMTRY(read_state(s));
       const int iters = s->h_state->iters;
       if (iters >= 1) {
-        CK(cudaMemcpyAsync(s->h_res, s->d_res + iters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+        PMTRY(publish_words(s, s->h_res, s->d_res + iters, sizeof(unsigned long long)));
         CK(cudaStreamSynchronize(s->stream));
         std::memcpy(res_out, s->h_res, 8);
       } else {
@@ -921,7 +929,7 @@ static int small_solve(pm_solver* s, int* iters_out, double* res_out) {
   PMTRY(read_state(s));
   const int iters = s->h_state->iters;
   if (iters >= 1) {
-    CK(cudaMemcpyAsync(s->h_res, s->d_res + iters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    PMTRY(publish_words(s, s->h_res, s->d_res + iters, sizeof(unsigned long long)));
     CK(cudaStreamSynchronize(s->stream));
     std::memcpy(res_out, s->h_res, 8);
   } else {
@@ -994,7 +1002,7 @@ extern "C" int pm_ppe_solve(pm_solver* s, pm_ppe_result* out) {
     if (K == 0) iters = 0;
     unsigned long long bits = 0;
     if (iters >= 1) {
-      CK(cudaMemcpyAsync(s->h_res, s->d_res + iters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+      PMTRY(publish_words(s, s->h_res, s->d_res + iters, sizeof(unsigned long long)));
       CK(cudaStreamSynchronize(s->stream));
       bits = s->h_res[0];
       std::memcpy(&res, &bits, 8);
@@ -1119,7 +1127,8 @@ extern "C" int pm_host_step_run(pm_solver* s, pm_ppe_result* r) {
   // results: p leaves through its own plane (the next solve overwrites both pressure buffers); u, v stay where
   // they are -- the next two steps use the other plane sets
   if (h.pdown_pending) CK(cudaStreamWaitEvent(s->stream, h.ev_pdown, 0));
-  CK(cudaMemcpyAsync(h.pout, s->pl[s->p_cur], s->plane * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+  k_copy_plane<<<1184, 256, 0, s->stream>>>(reinterpret_cast<const double2*>(s->pl[s->p_cur]), reinterpret_cast<double2*>(h.pout), s->plane / 2);
+  CKL(s);
   CK(cudaEventRecord(h.ev_step, s->stream));
   CK(cudaStreamWaitEvent(h.d2h, h.ev_step, 0));
   const HostPipe::Job& j = h.job[set];

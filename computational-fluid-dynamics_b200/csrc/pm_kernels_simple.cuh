@@ -477,6 +477,18 @@ __global__ void k_copy_corners(const __grid_constant__ KP k, const double* __res
   dst[pm_idx(k, jl, i)] = src[pm_idx(k, jl, i)];
 }
 
+// Small words device -> anywhere the device can address, pinned host memory included (zero-copy).  The solver's
+// state read-backs go this way instead of cudaMemcpyAsync: a copy-engine transfer of a few bytes would queue
+// behind the bulk host copies of pm_host_step_* on the same engine and stall the pressure solve for milliseconds.
+__global__ void k_publish_words(const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst, int nwords) {
+  for (int q = threadIdx.x; q < nwords; q += blockDim.x) dst[q] = src[q];
+  __threadfence_system();
+}
+// Plane-sized device copy on the SMs (128-bit), for the same reason.
+__global__ void k_copy_plane(const double2* __restrict__ src, double2* __restrict__ dst, size_t n2) {
+  for (size_t q = size_t(blockIdx.x) * blockDim.x + threadIdx.x; q < n2; q += size_t(gridDim.x) * blockDim.x) dst[q] = src[q];
+}
+
 // ---------------------------------------------------------------------------
 // synthetic state and layout conversion
 // ---------------------------------------------------------------------------

@@ -27,3 +27,29 @@ def run(up, down, reps=4):
 
 run(True, True, 1)
 print(f"H2D alone {run(True, False):.1f} GB/s; D2H alone {run(False, True):.1f} GB/s; both: {run(True, True):.1f} GB/s each direction")
+
+# The same with pitched 2-D copies of the shape pm_upload_slab / pm_download_slab use at 8192^2
+# (dense host rows of 8193 doubles <-> device rows of pitch 8224 doubles).
+from cuda.bindings import runtime as rt  # noqa: E402
+
+rows, cols, pitch = 8194, 8193, 8224
+hp_in, hp_out = h_in.data_ptr(), h_out.data_ptr()
+dp_in, dp_out = d_in.data_ptr(), d_out.data_ptr()
+K = rt.cudaMemcpyKind
+
+
+def run2d(up, down, reps=4):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        if up:
+            rt.cudaMemcpy2DAsync(dp_in, pitch * 8, hp_in, cols * 8, cols * 8, rows, K.cudaMemcpyHostToDevice, s1.cuda_stream)
+        if down:
+            rt.cudaMemcpy2DAsync(hp_out, cols * 8, dp_out, pitch * 8, cols * 8, rows, K.cudaMemcpyDeviceToHost, s2.cuda_stream)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return reps * rows * cols * 8 / dt / 1e9
+
+
+run2d(True, True, 1)
+print(f"2-D pitched: H2D alone {run2d(True, False):.1f} GB/s; D2H alone {run2d(False, True):.1f} GB/s; both: {run2d(True, True):.1f} GB/s each direction")
