@@ -49,7 +49,12 @@ struct pm_solver {
   int rows_alloc = 0;
   double* base = nullptr;  // PL_COUNT planes
   double* pl[PL_COUNT] = {};
-  int p_cur = PL_P0;       // plane holding the current pressure
+  int p_cur = PL_P0;       // plane holding the current pressure (natural layout)
+  // Tiled path: the solve ping-pongs between two buffers of its own in the split-row layout (pm_common.cuh).  The
+  // pressure is converted lazily: p_split / p_nat say which representation currently holds it.
+  double* tp[2] = {nullptr, nullptr};
+  int tp_cur = 0;
+  bool p_split = false, p_nat = true;
   uint8_t* mask = nullptr; // same geometry, bytes
   PpeState* d_state = nullptr;
   unsigned long long* d_res = nullptr;  // max_iters + 2 entries
@@ -229,6 +234,7 @@ static int destroy_impl(pm_solver* s) {
     cudaFree(s->hp.extra);
   }
   if (s->base) cudaFree(s->base);
+  if (s->tp[0]) cudaFree(s->tp[0]);
   if (s->mask) cudaFree(s->mask);
   if (s->d_state) cudaFree(s->d_state);
   if (s->d_res) cudaFree(s->d_res);
@@ -312,9 +318,13 @@ static int create_impl(pm_solver* s, const pm_config* cfg) {
                  (c.kernel_path == PM_PATH_TILED || (c.kernel_path == PM_PATH_AUTO && (c.nranks == 1 || nyl >= 2 * PM_PADR)));
   if (s->use_tiled) {
     std::string e;
-    if (!tiled_create(&s->tiled, c, k, s->pl[PL_P0], s->pl[PL_P1], s->rows_alloc, &e))
+    CK(cudaMalloc(&s->tp[0], s->plane * 2 * sizeof(double)));
+    CK(cudaMemsetAsync(s->tp[0], 0, s->plane * 2 * sizeof(double), s->stream));
+    s->tp[1] = s->tp[0] + s->plane;
+    if (!tiled_create(&s->tiled, c, k, s->tp[0], s->tp[1], s->rows_alloc, &e))
       return fail(s, PM_ERR_CUDA, "tiled path setup: %s", e.c_str());
     s->sweeps = s->tiled.sweeps;
+    s->kp.psh = s->tiled.psh;
   }
 
   if (c.nranks > 1) {
@@ -368,6 +378,31 @@ extern "C" int pm_sync(pm_solver* s) {
 }
 
 // ---------------------------------------------------------------------------
+// lazy conversion of the pressure between the natural planes and the split-row buffers of the tiled solve
+// ---------------------------------------------------------------------------
+static int convert_rows(pm_solver* s, const double* src, double* dst, int to_split) {
+  const dim3 b(128, 2), g((s->kp.pitch / 2 + 127) / 128, (s->rows_alloc + 1) / 2);
+  k_split_rows<<<g, b, 0, s->stream>>>(s->kp, src, dst, s->rows_alloc, to_split);
+  CKL(s);
+  return PM_OK;
+}
+static int ensure_p_natural(pm_solver* s) {  // before anything reads s->pl[s->p_cur]
+  if (s->use_tiled && !s->p_nat) {
+    PMTRY(convert_rows(s, s->tp[s->tp_cur], s->pl[s->p_cur], 0));
+    s->p_nat = true;
+  }
+  return PM_OK;
+}
+static int ensure_p_split(pm_solver* s) {  // before the tiled solve reads s->tp[s->tp_cur]
+  if (!s->p_split) {
+    PMTRY(convert_rows(s, s->pl[s->p_cur], s->tp[s->tp_cur], 1));
+    s->p_split = true;
+  }
+  return PM_OK;
+}
+static void p_natural_written(pm_solver* s) { s->p_nat = true; s->p_split = false; }
+
+// ---------------------------------------------------------------------------
 // data movement
 // ---------------------------------------------------------------------------
 // Local storage rows jl_a..jl_b of a field correspond to global rows j0+jl.
@@ -394,6 +429,7 @@ extern "C" int pm_upload(pm_solver* s, int field, const double* host, size_t cou
                        size_t(cols) * 8, size_t(jb - ja + 1), cudaMemcpyHostToDevice, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   if (field == PM_FIELD_F) s->f_max_valid = false;
+  if (field == PM_FIELD_P) p_natural_written(s);
   return PM_OK;
 }
 extern "C" int pm_download(pm_solver* s, int field, double* host, size_t count) {
@@ -404,6 +440,7 @@ extern "C" int pm_download(pm_solver* s, int field, double* host, size_t count) 
   if (!src) return fail(s, PM_ERR_INVALID_ARGUMENT, "unknown field %d", field);
   if (count != size_t(rows) * cols) return fail(s, PM_ERR_INVALID_ARGUMENT, "field %d expects %zu elements, got %zu", field, size_t(rows) * cols, count);
   CK(cudaSetDevice(s->device));
+  if (field == PM_FIELD_P) PMTRY(ensure_p_natural(s));
   int ja, jb;
   local_row_span(s, rows, false, &ja, &jb);
   const KP& k = s->kp;
@@ -433,6 +470,7 @@ static int slab_copy(pm_solver* s, int field, double* host, size_t count, bool t
   const size_t n = size_t(jb - ja + 1);
   if (count != n * cols) return fail(s, PM_ERR_INVALID_ARGUMENT, "slab of field %d expects %zu elements, got %zu", field, n * cols, count);
   CK(cudaSetDevice(s->device));
+  if (field == PM_FIELD_P && !to_device) PMTRY(ensure_p_natural(s));
   const KP& k = s->kp;
   if (to_device)
     CK(cudaMemcpy2DAsync(dev + pm_idx(k, ja, 0), size_t(k.pitch) * 8, host, size_t(cols) * 8, size_t(cols) * 8, n, cudaMemcpyHostToDevice, s->stream));
@@ -440,6 +478,7 @@ static int slab_copy(pm_solver* s, int field, double* host, size_t count, bool t
     CK(cudaMemcpy2DAsync(host, size_t(cols) * 8, dev + pm_idx(k, ja, 0), size_t(k.pitch) * 8, size_t(cols) * 8, n, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   if (to_device && field == PM_FIELD_F) s->f_max_valid = false;
+  if (to_device && field == PM_FIELD_P) p_natural_written(s);
   return PM_OK;
 }
 extern "C" int pm_upload_slab(pm_solver* s, int field, const double* host, size_t count) { return slab_copy(s, field, const_cast<double*>(host), count, true); }
@@ -474,7 +513,11 @@ extern "C" int pm_fill_zero(pm_solver* s) {
     PMTRY(pm_host_step_drain(s));
     CK(cudaMemsetAsync(s->hp.extra, 0, s->plane * 5 * sizeof(double), s->stream));
   }
+  if (s->tp[0]) CK(cudaMemsetAsync(s->tp[0], 0, s->plane * 2 * sizeof(double), s->stream));
   s->p_cur = PL_P0;
+  s->tp_cur = 0;
+  s->p_nat = true;
+  s->p_split = s->use_tiled;  // zero in either layout
   s->f_max_valid = false;
   return PM_OK;
 }
@@ -492,6 +535,7 @@ extern "C" int pm_fill_random_scaled(pm_solver* s, uint64_t seed, double amplitu
     k_fill_random<<<g, b, 0, s->stream>>>(k, field_plane(s, field), field, rows, cols, seed, amplitude);
     CKL(s);
   }
+  p_natural_written(s);
   s->f_max_valid = false;
   return PM_OK;
 }
@@ -617,11 +661,14 @@ extern "C" int pm_correct(pm_solver* s) {
   if (!s) return PM_ERR_INVALID_ARGUMENT;
   CK(cudaSetDevice(s->device));
   const KP& k = s->kp;
-  PMTRY(exchange_halo1(s, s->pl[s->p_cur]));
+  // after a tiled solve the pressure is read where the solve left it, in the split-row layout
+  const int psplit = s->use_tiled && s->p_split && !s->p_nat;
+  const double* p = psplit ? s->tp[s->tp_cur] : s->pl[s->p_cur];
+  PMTRY(exchange_halo1(s, const_cast<double*>(p)));
   if (s->cfg.exact_arith)
-    k_correct<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->pl[s->p_cur], s->mask, s->pl[PL_U], s->pl[PL_V]);
+    k_correct<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], p, s->mask, s->pl[PL_U], s->pl[PL_V], psplit);
   else
-    k_correct<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->pl[s->p_cur], s->mask, s->pl[PL_U], s->pl[PL_V]);
+    k_correct<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], p, s->mask, s->pl[PL_U], s->pl[PL_V], psplit);
   CKL(s);
   return PM_OK;
 }
@@ -740,7 +787,7 @@ static int tiled_pass(pm_solver* s, int in, int m0, int nsw, int force) {
 static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
   const TiledPlan& pl = s->tiled;
   const int K = s->cfg.max_iters, T = pl.sweeps;
-  const int in0 = s->p_cur == PL_P0 ? 0 : 1;
+  const int in0 = s->tp_cur;
   CK(tiled_begin_solve(&pl, s->stream));
   if (s->cfg.nranks > 1) {  // halos of the inputs: f once per solve, p as deep as one pass reaches
     PMTRY(exchange_halo(s, s->pl[PL_F], pl.halo, s->stream));
@@ -778,7 +825,9 @@ static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
     iters = K;
     buf = in0 ^ (n & 1);
   }
-  s->p_cur = buf ? PL_P1 : PL_P0;
+  s->tp_cur = buf;
+  s->p_split = true;
+  s->p_nat = false;
   if (iters >= 1) {
     PMTRY(publish_words(s, s->h_res, s->d_res + iters, sizeof(unsigned long long)));
     CK(cudaStreamSynchronize(s->stream));
@@ -962,10 +1011,19 @@ extern "C" int pm_ppe_solve(pm_solver* s, pm_ppe_result* out) {
     // Only the buffer the solve starts from needs clearing: the first pass overwrites every interior cell of the
     // other one, and in the cavity nothing ever writes a ghost or pad cell of either buffer (they stay 0 from
     // pm_create / pm_fill_zero; halo rows between slabs are re-exchanged every pass).
-    CK(cudaMemsetAsync(s->pl[s->p_cur], 0, s->plane * sizeof(double), s->stream));
+    if (s->use_tiled) {
+      CK(cudaMemsetAsync(s->tp[s->tp_cur], 0, s->plane * sizeof(double), s->stream));
+      s->p_split = true;
+      s->p_nat = false;
+    } else {
+      CK(cudaMemsetAsync(s->pl[s->p_cur], 0, s->plane * sizeof(double), s->stream));
+    }
+  } else if (s->use_tiled) {
+    PMTRY(ensure_p_split(s));  // warm start (channel-01.cpp:636)
   }
   if (!cav && !s->use_small && (c.ppe_method == PM_PPE_JACOBI || s->use_tiled)) {  // ping-pong solves: both buffers carry the corner ghosts
-    k_copy_corners<<<1, 32, 0, s->stream>>>(k, s->pl[s->p_cur], s->pl[s->p_cur == PL_P0 ? PL_P1 : PL_P0]);
+    if (s->use_tiled) k_copy_corners<<<1, 32, 0, s->stream>>>(k, s->tp[s->tp_cur], s->tp[s->tp_cur ^ 1], 1);
+    else k_copy_corners<<<1, 32, 0, s->stream>>>(k, s->pl[s->p_cur], s->pl[s->p_cur == PL_P0 ? PL_P1 : PL_P0], 0);
     CKL(s);
   }
   CK(cudaMemsetAsync(s->d_res, 0, size_t(c.max_iters + 2) * sizeof(unsigned long long), s->stream));
@@ -1127,8 +1185,12 @@ extern "C" int pm_host_step_run(pm_solver* s, pm_ppe_result* r) {
   // results: p leaves through its own plane (the next solve overwrites both pressure buffers); u, v stay where
   // they are -- the next two steps use the other plane sets
   if (h.pdown_pending) CK(cudaStreamWaitEvent(s->stream, h.ev_pdown, 0));
-  k_copy_plane<<<1184, 256, 0, s->stream>>>(reinterpret_cast<const double2*>(s->pl[s->p_cur]), reinterpret_cast<double2*>(h.pout), s->plane / 2);
-  CKL(s);
+  if (s->use_tiled && !s->p_nat) {
+    PMTRY(convert_rows(s, s->tp[s->tp_cur], h.pout, 0));  // straight from the solve's split-row buffer
+  } else {
+    k_copy_plane<<<1184, 256, 0, s->stream>>>(reinterpret_cast<const double2*>(s->pl[s->p_cur]), reinterpret_cast<double2*>(h.pout), s->plane / 2);
+    CKL(s);
+  }
   CK(cudaEventRecord(h.ev_step, s->stream));
   CK(cudaStreamWaitEvent(h.d2h, h.ev_step, 0));
   const HostPipe::Job& j = h.job[set];

@@ -22,6 +22,7 @@ struct KP {
   int pitch, padr; // doubles per row; pad rows
   int case_id, has_mask, first_rank, last_rank;
   int inlet_j_max;
+  int psh;         // split-row layout of the tiled solve: column shift (0 or 2), see pm_split_col
   // constants, each computed on the host with the reference's own expression (see pm_capi.cu)
   double idx, idy, idx2, idy2;  // 1/dx, 1/dy, 1/(dx*dx), 1/(dy*dy)
   double hh;                    // cavity: grid_spacing*grid_spacing   (cavity-01.cpp:653)
@@ -39,6 +40,22 @@ struct KP {
 
 __host__ __device__ __forceinline__ size_t pm_idx(const KP& k, int jl, int i) {
   return size_t(k.padr + jl) * size_t(k.pitch) + size_t(PM_OFFC + i);
+}
+
+// Split-row layout of the pressure buffers of the tiled solve: within each row of `pitch` doubles the even
+// storage columns come first, then the odd ones, so that one TMA box {64 pairs, 2 parities, rows} lands in
+// shared memory in the order the sweeps exchange neighbours in.  Column c sits at
+//   (c & 1) * pitch/2 + ((c + psh) >> 1)  (mod pitch/2),
+// where the shift psh (0 or 2, chosen from the halo depth) makes the first pair of every tile even: TMA needs
+// 16-byte aligned box rows.  The columns that wrap around are pad columns.
+__host__ __device__ __forceinline__ int pm_split_col(const KP& k, int c) {
+  const int half = k.pitch >> 1;
+  int h = (c + k.psh) >> 1;
+  if (h >= half) h -= half;
+  return (c & 1) * half + h;
+}
+__host__ __device__ __forceinline__ size_t pm_sidx(const KP& k, int jl, int i) {
+  return size_t(k.padr + jl) * size_t(k.pitch) + size_t(pm_split_col(k, PM_OFFC + i));
 }
 
 // ---- arithmetic policies -------------------------------------------------

@@ -412,22 +412,25 @@ template <class A>
 __global__ void __launch_bounds__(PM_BX* PM_BY)
     k_correct(const __grid_constant__ KP k, const double* __restrict__ us, const double* __restrict__ vs,
               const double* __restrict__ p, const uint8_t* __restrict__ M, double* __restrict__ u,
-              double* __restrict__ v) {
+              double* __restrict__ v, int psplit) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
   if (i > k.nx || jl > k.nyl) return;
   const int j = k.j0 + jl;
   const size_t c = pm_idx(k, jl, i);
-  const double pc = p[c];
+  // psplit: p is the final buffer of the tiled solve, still in its split-row layout
+  const size_t pc_i = psplit ? pm_sidx(k, jl, i) : c, pe_i = psplit ? pm_sidx(k, jl, i + 1) : c + 1,
+               pn_i = psplit ? pm_sidx(k, jl + 1, i) : c + k.pitch;
+  const double pc = p[pc_i];
   bool fl_c = true, fl_e = true, fl_n = true;
   if (k.has_mask) { fl_c = M[c]; fl_e = M[c + 1]; fl_n = M[c + k.pitch]; }
   if (i <= k.nx - 1) {
     const bool valid = (i == k.nx - 1) || fl_c || fl_e;
-    u[c] = valid ? A::sub(us[c], A::mul(k.cu, A::sub(p[c + 1], pc))) : 0.0;
+    u[c] = valid ? A::sub(us[c], A::mul(k.cu, A::sub(p[pe_i], pc))) : 0.0;
   }
   if (j <= k.ny - 1) {
     const bool valid = (j == k.ny - 1) || fl_c || fl_n;
-    v[c] = valid ? A::sub(vs[c], A::mul(k.cv, A::sub(p[c + k.pitch], pc))) : 0.0;
+    v[c] = valid ? A::sub(vs[c], A::mul(k.cv, A::sub(p[pn_i], pc))) : 0.0;
   }
 }
 
@@ -469,12 +472,13 @@ __global__ void k_sum_partials(const double* __restrict__ partial, int n, PpeSta
 
 // The four corner ghosts of p are never written by any sweep; a ping-pong (Jacobi) solve carries
 // them into the second buffer so both hold the same field outside the stencil's reach.
-__global__ void k_copy_corners(const __grid_constant__ KP k, const double* __restrict__ src, double* __restrict__ dst) {
+__global__ void k_copy_corners(const __grid_constant__ KP k, const double* __restrict__ src, double* __restrict__ dst, int split) {
   const int t = threadIdx.x;
   if (t >= 4) return;
   const int jl = (t & 2) ? k.nyl + 1 : 0, i = (t & 1) ? k.nx + 1 : 0;
   if ((jl == 0 && !k.first_rank) || (jl != 0 && !k.last_rank)) return;
-  dst[pm_idx(k, jl, i)] = src[pm_idx(k, jl, i)];
+  const size_t q = split ? pm_sidx(k, jl, i) : pm_idx(k, jl, i);  // split: buffers of the tiled solve (split-row layout)
+  dst[q] = src[q];
 }
 
 // Small words device -> anywhere the device can address, pinned host memory included (zero-copy).  The solver's

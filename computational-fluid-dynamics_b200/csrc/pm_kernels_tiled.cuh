@@ -3,9 +3,12 @@
 // One launch ("pass") advances the pressure field by up to T sweeps (temporal blocking) and
 // produces the infinity-norm residual of every iterate it passes through, moving p once in and
 // once out of HBM and f once in:
-//   * the (TY+2H) x 128 tile of p around a (TY x TX) output block is staged into shared memory by
-//     ONE TMA tensor load (cp.async.bulk.tensor.2d, zero-filled outside the allocation) signalled
-//     on an mbarrier; f goes straight from HBM into registers with 128-bit row loads meanwhile;
+//   * the pressure buffers of the solve live in HBM in the split-row layout (pm_common.cuh: even storage
+//     columns of a row first, then the odd ones); the (TY+2H) x 128 tile of p around a (TY x TX) output
+//     block is staged into shared memory by ONE TMA tensor load (cp.async.bulk.tensor.3d over
+//     {pair, parity, row}, zero-filled outside the allocation) signalled on an mbarrier and arrives in
+//     the order the sweeps exchange neighbours in -- no rewrite, no barrier before the first half-sweep;
+//     f goes straight from HBM into registers with 128-bit row loads meanwhile;
 //   * every thread keeps its RPT x 2 cells of p and f in registers for the whole pass; shared
 //     memory only carries the values neighbouring threads exchange (one 64-bit load and one
 //     64-bit store per cell update), so the sweeps are bounded by the FP64 pipe, not by smem;
@@ -56,6 +59,11 @@ struct TileCfg {
   static_assert(TX > 0 && TY > 0, "halo too deep for the tile");
   static_assert(RPT % 2 == 0 && TY % 2 == 0, "PAR0 (colour of a thread's first row) must not depend on the segment or the tile row");
   static_assert(H <= PM_PADR, "halo deeper than the pad rows of the planes");
+  static_assert(H % 2 == 0 && TX % 4 == 0 && (PM_OFFC + 1) % 2 == 0 && PM_OFFC + 1 >= H,
+                "the first storage column of every tile must be even (it is the .x cell of lane 0), non-negative, and the same mod 4 for all tiles");
+  // shift of the split-row layout that makes (first storage column + PSH) / 2 even: 16-byte aligned TMA box rows
+  static constexpr int PSH = (4 - ((PM_OFFC + 1 - H) & 3)) & 3;
+  static_assert(PSH == 0 || PSH == 2, "");
 };
 
 // ---- mbarrier / TMA primitives (sm_90+ PTX; SASS: SYNCS.*, UTMALDG) -----------------------------
@@ -77,11 +85,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
         : "memory");
   } while (!ok);
 }
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int cx, int cy) {
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int cx, int cy, int cz) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       :
-      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(cx), "r"(cy)
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(cx), "r"(cy), "r"(cz)
       : "memory");
 }
 
@@ -574,49 +582,40 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
   }
   mbar_wait(bar, phase);
   PM_PROF(1);  // wait for the TMA tile
-  {  // TMA delivered natural row order: take the own cells, then rewrite the tile in the split-row layout
-    const double* tn = tile + rr0 * SW + c0;
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      const double2 v = *reinterpret_cast<const double2*>(tn + r * SW);
-      c.p0[r] = v.x;
-      c.p1[r] = v.y;
-    }
-  }
+  // The tile arrived in the split-row layout: every thread takes its own cells; neighbours are read in place.
+  // No barrier: before the first half-sweep's barrier a thread only ever writes cells it owns.
   double* tpx = tile + rr0 * SW + q;
   double* tpy = tpx + SW / 2;
-  __syncthreads();  // every thread holds its cells
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
-    tpx[r * SW] = c.p0[r];
-    tpy[r * SW] = c.p1[r];
+    c.p0[r] = tpx[r * SW];
+    c.p1[r] = tpy[r * SW];
   }
-  __syncthreads();
 
-  PM_PROF(2);  // own cells (this waits for the f registers too), split-row rewrite
+  PM_PROF(2);  // own cells
   // the residual-only pass (nsw == 0) commits nothing and takes the general code path
   if (interior && nsw > 0) run_sweeps<A, FORM, METHOD, T, true, PAR0>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red);
   else run_sweeps<A, FORM, METHOD, T, false, PAR0>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red);
 
   PM_PROF(3);  // the sweeps
-  // ---- write the output block: 128-bit stores, plus the wall ghosts its cells own ----
+  // ---- write the output block (split-row layout: .x cells to the even half of the row, .y cells to the odd
+  // half, consecutive lanes to consecutive doubles), plus the wall ghosts its cells own ----
   if (nsw > 0) {
-    double* op = pout + pm_idx(k, jl0, i0);
     const int P = k.pitch;
+    double* ox = pout + size_t(k.padr + jl0) * size_t(P) + size_t((PM_OFFC + i0 + k.psh) >> 1);  // PM_OFFC + i0 is even
+    double* oy = ox + (P >> 1);
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
       if (!((mO >> r) & 1u)) continue;
-      double* o = op + size_t(r) * P;
-      if (colO0 && colO1) *reinterpret_cast<double2*>(o) = make_double2(c.p0[r], c.p1[r]);
-      else if (colO0) o[0] = c.p0[r];
-      else if (colO1) o[1] = c.p1[r];
+      if (colO0) ox[size_t(r) * P] = c.p0[r];
+      if (colO1) oy[size_t(r) * P] = c.p1[r];
       if (FORM == 1 && !interior) {
-        const int j = jg0 + r;
-        if (colO0 && i0 == 1) o[-1] = c.p0[r];
-        if (colO0 && i0 == k.nx) o[1] = 0.0;
-        if (colO1 && i0 + 1 == k.nx) o[2] = 0.0;
-        if (j == 1) { if (colO0) o[-P] = c.p0[r]; if (colO1) o[1 - P] = c.p1[r]; }
-        if (j == k.ny) { if (colO0) o[P] = c.p0[r]; if (colO1) o[1 + P] = c.p1[r]; }
+        const int j = jg0 + r, jl = jl0 + r;
+        if (colO0 && i0 == 1) pout[pm_sidx(k, jl, 0)] = c.p0[r];
+        if (colO0 && i0 == k.nx) pout[pm_sidx(k, jl, k.nx + 1)] = 0.0;
+        if (colO1 && i0 + 1 == k.nx) pout[pm_sidx(k, jl, k.nx + 1)] = 0.0;
+        if (j == 1) { if (colO0) pout[pm_sidx(k, jl - 1, i0)] = c.p0[r]; if (colO1) pout[pm_sidx(k, jl - 1, i0 + 1)] = c.p1[r]; }
+        if (j == k.ny) { if (colO0) pout[pm_sidx(k, jl + 1, i0)] = c.p0[r]; if (colO1) pout[pm_sidx(k, jl + 1, i0 + 1)] = c.p1[r]; }
       }
     }
   }
@@ -668,7 +667,7 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
     mbar_init(&mbar, 1);
     fence_mbar_init();
     mbar_expect_tx(&mbar, C::SH * C::SW * 8);
-    tma_load_2d(tile, &tmap_in, &mbar, PM_OFFC + 1 + bx * C::TX - C::H, k.padr + 1 + by * C::TY - C::H);
+    tma_load_3d(tile, &tmap_in, &mbar, (PM_OFFC + 1 + bx * C::TX - C::H + k.psh) >> 1, 0, k.padr + 1 + by * C::TY - C::H);
   }
   StopWords<T> stopw;
   if (!force) stopw = stop_words_load<T>(st, res_bits, m0);
@@ -677,6 +676,25 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
   if (tid == 0) atomicAdd(&g_tile_prof[5], (unsigned long long)(clock64() - prof_k));
 #endif
   tile_process<A, FORM, METHOD, T, PAR0>(k, tile, &mbar, 0u, red, pout, f, st, res_bits, fold_part, m0, nsw, bx, by, stopw, !force);
+}
+
+// Whole-plane conversion between the natural and the split-row layout (a permutation inside every row).
+// to_split: dst[row][split(c)] = src[row][c]; otherwise dst[row][c] = src[row][split(c)].  One thread per column pair.
+__global__ void k_split_rows(const __grid_constant__ KP k, const double* __restrict__ src, double* __restrict__ dst, int rows, int to_split) {
+  const int pr = blockIdx.x * blockDim.x + threadIdx.x;  // pair index
+  const int row = blockIdx.y * blockDim.y + threadIdx.y;
+  const int half = k.pitch >> 1;
+  if (pr >= half || row >= rows) return;
+  const size_t base = size_t(row) * size_t(k.pitch);
+  int h = pr + (k.psh >> 1);  // where the pair (2 pr, 2 pr + 1) sits in either half, see pm_split_col
+  if (h >= half) h -= half;
+  if (to_split) {
+    const double2 v = *reinterpret_cast<const double2*>(src + base + 2 * pr);
+    dst[base + h] = v.x;
+    dst[base + half + h] = v.y;
+  } else {
+    *reinterpret_cast<double2*>(dst + base + 2 * pr) = make_double2(src[base + h], src[base + half + h]);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -688,6 +706,7 @@ struct TiledPlan {
   int tx = 0, ty = 0;   // output block
   int tiles_x = 0, tiles_y = 0;
   int smem_bytes = 0;
+  int psh = 0;          // column shift of the split-row layout (KP::psh)
   CUtensorMap map[2];   // p ping / p pong
   double* p[2] = {nullptr, nullptr};
   const void* kernel = nullptr;
@@ -714,7 +733,7 @@ static const void* tiled_kernel_ptr(int par0) {
 template <int METHOD, int T>
 static void tiled_geometry(TiledPlan* pl) {
   using C = TileCfg<METHOD, T>;
-  pl->sweeps = T; pl->halo = C::H; pl->tx = C::TX; pl->ty = C::TY; pl->smem_bytes = C::SMEM_BYTES;
+  pl->sweeps = T; pl->halo = C::H; pl->tx = C::TX; pl->ty = C::TY; pl->smem_bytes = C::SMEM_BYTES; pl->psh = C::PSH;
 }
 
 template <class A, int FORM>
@@ -753,12 +772,12 @@ static inline bool tiled_create(TiledPlan* pl, const pm_config& c, const KP& k, 
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
   if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) { *err = "cuTensorMapEncodeTiled not available from the driver"; return false; }
   PFN_tmapEncodeTiled encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
-  for (int b = 0; b < 2; ++b) {
-    const cuuint64_t gdim[2] = {cuuint64_t(k.pitch), cuuint64_t(rows_alloc)};
-    const cuuint64_t gstr[1] = {cuuint64_t(k.pitch) * 8};
-    const cuuint32_t box[2] = {128u, cuuint32_t(TileCfg<0, 1>::SH)};
-    const cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = encode(&pl->map[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, pl->p[b], gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  for (int b = 0; b < 2; ++b) {  // {pair, parity, row} view of a split-row plane
+    const cuuint64_t gdim[3] = {cuuint64_t(k.pitch / 2), 2u, cuuint64_t(rows_alloc)};
+    const cuuint64_t gstr[2] = {cuuint64_t(k.pitch / 2) * 8, cuuint64_t(k.pitch) * 8};
+    const cuuint32_t box[3] = {64u, 2u, cuuint32_t(TileCfg<0, 1>::SH)};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = encode(&pl->map[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, pl->p[b], gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)); return false; }
   }
