@@ -112,6 +112,8 @@ static int publish_words(pm_solver* s, void* dst, const void* src, size_t bytes)
 
 static inline dim3 cell_block() { return dim3(PM_BX, PM_BY); }
 static inline dim3 cell_grid(const KP& k) { return dim3((k.nx + PM_BX - 1) / PM_BX, (k.nyl + PM_BY - 1) / PM_BY); }
+static inline dim3 rows_block() { return dim3(PM_RX, PM_RY); }  // k_*_rows: two cells per thread
+static inline dim3 rows_grid(const KP& k) { return dim3(((k.nx + 1) / 2 + PM_RX - 1) / PM_RX, (k.nyl + PM_RY - 1) / PM_RY); }
 static inline dim3 half_grid(const KP& k) { return dim3(((k.nx + 1) / 2 + PM_BX - 1) / PM_BX, (k.nyl + PM_BY - 1) / PM_BY); }
 
 static void field_dims(const pm_solver* s, int field, int* rows, int* cols) {
@@ -600,7 +602,10 @@ extern "C" int pm_predict(pm_solver* s) {
   const KP& k = s->kp;
   PMTRY(exchange_halo1(s, s->pl[PL_U]));
   PMTRY(exchange_halo1(s, s->pl[PL_V]));
-  if (s->cfg.exact_arith)
+  if (!k.has_mask) {  // unmasked: two cells per thread, 128-bit rows
+    if (s->cfg.exact_arith) k_predict_rows<Exact><<<rows_grid(k), rows_block(), 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->pl[PL_US], s->pl[PL_VS]);
+    else k_predict_rows<Fast><<<rows_grid(k), rows_block(), 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->pl[PL_US], s->pl[PL_VS]);
+  } else if (s->cfg.exact_arith)
     k_predict<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->mask, s->pl[PL_US], s->pl[PL_VS]);
   else
     k_predict<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->mask, s->pl[PL_US], s->pl[PL_VS]);
@@ -617,7 +622,13 @@ extern "C" int pm_source(pm_solver* s) {
   PMTRY(exchange_halo1(s, s->pl[PL_VS]));  // f[1][i] reads v*[0][i] of the slab below
   CK(cudaMemsetAsync(&s->d_state->maxf_bits, 0, 2 * sizeof(unsigned long long), s->stream));
   double* partial = (!cav && !exact) ? s->d_partial : nullptr;
-  if (exact)
+  int n_partial = s->n_partial;  // blocks that wrote a partial sum
+  if (!k.has_mask) {
+    const dim3 g = rows_grid(k);
+    n_partial = int(g.x * g.y);
+    if (exact) k_source_rows<Exact><<<g, rows_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->pl[PL_F], s->d_state, partial);
+    else k_source_rows<Fast><<<g, rows_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->pl[PL_F], s->d_state, partial);
+  } else if (exact)
     k_source<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->mask, s->pl[PL_F], s->d_state, partial);
   else
     k_source<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->mask, s->pl[PL_F], s->d_state, partial);
@@ -632,7 +643,7 @@ extern "C" int pm_source(pm_solver* s) {
     if (exact) return fail(s, PM_ERR_UNSUPPORTED, "exact_arith keeps the reference's serial source sum, which does not shard; use exact_arith=0 with nranks > 1");
     std::string e;
     if (!pm_nccl_allreduce_max_u64(&s->nccl, s->stream, &s->d_state->maxf_bits, 1, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
-    k_sum_partials<<<1, 1024, 0, s->stream>>>(s->d_partial, s->n_partial, s->d_state);  // local sum -> ke_sum scratch
+    k_sum_partials<<<1, 1024, 0, s->stream>>>(s->d_partial, n_partial, s->d_state);  // local sum -> ke_sum scratch
     CKL(s);
     if (!pm_nccl_allreduce_sum_f64(&s->nccl, s->stream, &s->d_state->ke_sum, 1, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
     k_mean_from_sum<<<1, 1, 0, s->stream>>>(k.fluid_count_global, s->d_state);
@@ -648,7 +659,7 @@ extern "C" int pm_source(pm_solver* s) {
     CKL(s);
     k_sub_mean<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
   } else {
-    k_mean_from_partials<<<1, 1024, 0, s->stream>>>(s->d_partial, s->n_partial, k.fluid_count_global, s->d_state);
+    k_mean_from_partials<<<1, 1024, 0, s->stream>>>(s->d_partial, n_partial, k.fluid_count_global, s->d_state);
     CKL(s);
     k_sub_mean<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
   }
@@ -665,7 +676,10 @@ extern "C" int pm_correct(pm_solver* s) {
   const int psplit = s->use_tiled && s->p_split && !s->p_nat;
   const double* p = psplit ? s->tp[s->tp_cur] : s->pl[s->p_cur];
   PMTRY(exchange_halo1(s, const_cast<double*>(p)));
-  if (s->cfg.exact_arith)
+  if (!k.has_mask) {
+    if (s->cfg.exact_arith) k_correct_rows<Exact><<<rows_grid(k), rows_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], p, s->pl[PL_U], s->pl[PL_V], psplit);
+    else k_correct_rows<Fast><<<rows_grid(k), rows_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], p, s->pl[PL_U], s->pl[PL_V], psplit);
+  } else if (s->cfg.exact_arith)
     k_correct<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], p, s->mask, s->pl[PL_U], s->pl[PL_V], psplit);
   else
     k_correct<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], p, s->mask, s->pl[PL_U], s->pl[PL_V], psplit);

@@ -86,6 +86,42 @@ __global__ void k_bc_solid(const __grid_constant__ KP k, const uint8_t* __restri
 // k2+k3  predictor: u* and v* in one pass (cavity-01.cpp:553-602; channel-01.cpp:553-602;
 //        backwards_step-01.cpp:752-819)
 // ---------------------------------------------------------------------------
+// u* at the east face of cell (j, i).  uc = u[j][i], uw/ue_ = u[j][i-1] / u[j][i+1], uN/uS = u[j+1][i] / u[j-1][i];
+// vc = v[j][i], ve_ = v[j][i+1], vS = v[j-1][i], vSE = v[j-1][i+1].
+template <class A>
+__device__ __forceinline__ double pred_u(const KP& k, double uc, double uw, double ue_, double uN, double uS, double vc, double ve_,
+                                         double vS, double vSE) {
+  const double t2 = A::mul(2.0, uc);
+  const double diff = A::mul(k.nu, A::add(A::mul(A::add(A::sub(ue_, t2), uw), k.idx2), A::mul(A::add(A::sub(uN, t2), uS), k.idy2)));
+  const double ue = A::mul(0.5, A::add(uc, ue_));
+  const double uwf = A::mul(0.5, A::add(uw, uc));
+  const double cx = A::mul(A::sub(A::mul(ue, ue), A::mul(uwf, uwf)), k.idx);
+  const double vn = A::mul(0.5, A::add(vc, ve_));
+  const double vsf = A::mul(0.5, A::add(vS, vSE));
+  const double un = A::mul(0.5, A::add(uN, uc));
+  const double usf = A::mul(0.5, A::add(uS, uc));
+  const double cy = A::mul(A::sub(A::mul(vn, un), A::mul(vsf, usf)), k.idy);
+  return A::add(uc, A::mul(k.dt, A::sub(A::sub(diff, cx), cy)));
+}
+// v* at the north face of cell (j, i).  vc = v[j][i], ve_/vw_ = v[j][i+1] / v[j][i-1], vN/vS = v[j+1][i] / v[j-1][i];
+// uc = u[j][i], uN = u[j+1][i], uw = u[j][i-1], uNW = u[j+1][i-1].
+template <class A>
+__device__ __forceinline__ double pred_v(const KP& k, double vc, double ve_, double vw_, double vN, double vS, double uc, double uN,
+                                         double uw, double uNW) {
+  const double t2 = A::mul(2.0, vc);
+  const double diff = A::mul(k.nu, A::add(A::mul(A::add(A::sub(ve_, t2), vw_), k.idx2), A::mul(A::add(A::sub(vN, t2), vS), k.idy2)));
+  const double vn = A::mul(0.5, A::add(vc, vN));
+  const double vsf = A::mul(0.5, A::add(vS, vc));
+  const double cy = A::mul(A::sub(A::mul(vn, vn), A::mul(vsf, vsf)), k.idy);
+  const double ue = A::mul(0.5, A::add(uc, uN));
+  const double uwf = A::mul(0.5, A::add(uw, uNW));
+  const double ve = A::mul(0.5, A::add(vc, ve_));
+  const double vw = A::mul(0.5, A::add(vw_, vc));
+  const double cx = A::mul(A::sub(A::mul(ue, ve), A::mul(uwf, vw)), k.idx);
+  return A::add(vc, A::mul(k.dt, A::sub(A::sub(diff, cy), cx)));
+}
+
+// General kernel (any case, obstacle mask): one thread per cell.
 template <class A>
 __global__ void __launch_bounds__(PM_BX* PM_BY)
     k_predict(const __grid_constant__ KP k, const double* __restrict__ u, const double* __restrict__ v,
@@ -103,42 +139,45 @@ __global__ void __launch_bounds__(PM_BX* PM_BY)
   const double ve_ = v[c + 1], vw_ = v[c - 1];
   bool fl_c = true, fl_e = true, fl_n = true;
   if (k.has_mask) { fl_c = M[c]; fl_e = M[c + 1]; fl_n = M[c + P]; }
-  if (do_u) {
-    double r = 0.0;
-    if (fl_c || fl_e) {
-      const double t2 = A::mul(2.0, uc);
-      const double diff = A::mul(k.nu, A::add(A::mul(A::add(A::sub(ue_, t2), uw), k.idx2),
-                                              A::mul(A::add(A::sub(uN, t2), uS), k.idy2)));
-      const double ue = A::mul(0.5, A::add(uc, ue_));
-      const double uwf = A::mul(0.5, A::add(uw, uc));
-      const double cx = A::mul(A::sub(A::mul(ue, ue), A::mul(uwf, uwf)), k.idx);
-      const double vn = A::mul(0.5, A::add(vc, ve_));
-      const double vsf = A::mul(0.5, A::add(vS, v[c - P + 1]));
-      const double un = A::mul(0.5, A::add(uN, uc));
-      const double usf = A::mul(0.5, A::add(uS, uc));
-      const double cy = A::mul(A::sub(A::mul(vn, un), A::mul(vsf, usf)), k.idy);
-      r = A::add(uc, A::mul(k.dt, A::sub(A::sub(diff, cx), cy)));
-    }
-    us[c] = r;
-  }
-  if (do_v) {
-    double r = 0.0;
-    if (fl_c || fl_n) {
-      const double vN = v[c + P];
-      const double t2 = A::mul(2.0, vc);
-      const double diff = A::mul(k.nu, A::add(A::mul(A::add(A::sub(ve_, t2), vw_), k.idx2),
-                                              A::mul(A::add(A::sub(vN, t2), vS), k.idy2)));
-      const double vn = A::mul(0.5, A::add(vc, vN));
-      const double vsf = A::mul(0.5, A::add(vS, vc));
-      const double cy = A::mul(A::sub(A::mul(vn, vn), A::mul(vsf, vsf)), k.idy);
-      const double ue = A::mul(0.5, A::add(uc, uN));
-      const double uwf = A::mul(0.5, A::add(uw, u[c + P - 1]));
-      const double ve = A::mul(0.5, A::add(vc, ve_));
-      const double vw = A::mul(0.5, A::add(vw_, vc));
-      const double cx = A::mul(A::sub(A::mul(ue, ve), A::mul(uwf, vw)), k.idx);
-      r = A::add(vc, A::mul(k.dt, A::sub(A::sub(diff, cy), cx)));
-    }
-    vs[c] = r;
+  if (do_u) us[c] = (fl_c || fl_e) ? pred_u<A>(k, uc, uw, ue_, uN, uS, vc, ve_, vS, v[c - P + 1]) : 0.0;
+  if (do_v) vs[c] = (fl_c || fl_n) ? pred_v<A>(k, vc, ve_, vw_, v[c + P], vS, uc, uN, uw, u[c + P - 1]) : 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// Row kernels for the unmasked cases (cavity, channel): two cells per thread -- columns i, i+1 with i odd, so the
+// pair starts at an even storage column -- every field moved with 128-bit loads and stores, the same per-cell
+// expression trees as the general kernels.  Block 128 x 2 threads = 256 columns x 2 rows.
+// ---------------------------------------------------------------------------
+#define PM_RX 128
+#define PM_RY 2
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+
+template <class A>
+__global__ void __launch_bounds__(PM_RX* PM_RY)
+    k_predict_rows(const __grid_constant__ KP k, const double* __restrict__ u, const double* __restrict__ v, double* __restrict__ us,
+                   double* __restrict__ vs) {
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x) + 1;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > k.nx || jl > k.nyl) return;
+  const int j = k.j0 + jl, P = k.pitch;
+  const size_t c = pm_idx(k, jl, i);
+  // the reads past column nx (u) / nx+1 (v) land in the zeroed pad columns of the plane and are never used
+  const double2 U = ld2(u + c), UN = ld2(u + c + P), US = ld2(u + c - P);
+  const double2 V = ld2(v + c), VN = ld2(v + c + P), VS = ld2(v + c - P);
+  const double uW = u[c - 1], uE2 = u[c + 2], uNW = u[c + P - 1];
+  const double vW = v[c - 1], vE2 = v[c + 2], vSE2 = v[c - P + 2];
+  const bool a_u = i <= k.nx - 1, b_u = i + 1 <= k.nx - 1;  // u* columns 1..nx-1
+  const bool a_v = j <= k.ny - 1, b_v = a_v && i + 1 <= k.nx;  // v* rows 1..ny-1, columns 1..nx
+  const double ua = pred_u<A>(k, U.x, uW, U.y, UN.x, US.x, V.x, V.y, VS.x, VS.y);
+  const double ub = pred_u<A>(k, U.y, U.x, uE2, UN.y, US.y, V.y, vE2, VS.y, vSE2);
+  if (a_u && b_u) st2(us + c, ua, ub);
+  else if (a_u) us[c] = ua;
+  if (a_v) {
+    const double va = pred_v<A>(k, V.x, V.y, vW, VN.x, VS.x, U.x, UN.x, uW, uNW);
+    const double vb = pred_v<A>(k, V.y, vE2, V.x, VN.y, VS.y, U.y, UN.y, U.x, UN.x);
+    if (b_v) st2(vs + c, va, vb);
+    else vs[c] = va;
   }
 }
 
@@ -169,6 +208,39 @@ __global__ void __launch_bounds__(PM_BX* PM_BY)
   if (threadIdx.x == 0 && threadIdx.y == 0) atomic_max_nonneg(&st->maxf_bits, m);
   if (partial) {
     const double s = block_sum(val, sh);
+    if (threadIdx.x == 0 && threadIdx.y == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+// Row version for the unmasked cases (see k_predict_rows).
+template <class A>
+__global__ void __launch_bounds__(PM_RX* PM_RY)
+    k_source_rows(const __grid_constant__ KP k, const double* __restrict__ us, const double* __restrict__ vs, double* __restrict__ f,
+                  PpeState* __restrict__ st, double* __restrict__ partial /* one per block, or null */) {
+  __shared__ double sh[32];
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x) + 1;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  double a = 0.0, sum = 0.0;
+  if (i <= k.nx && jl <= k.nyl) {
+    const size_t c = pm_idx(k, jl, i);
+    const double2 U = ld2(us + c), V = ld2(vs + c), VS = ld2(vs + c - k.pitch);
+    const double uW = us[c - 1];
+    const double fa = A::mul(k.src_coef, A::add(A::mul(A::sub(U.x, uW), k.idx), A::mul(A::sub(V.x, VS.x), k.idy)));
+    if (i + 1 <= k.nx) {
+      const double fb = A::mul(k.src_coef, A::add(A::mul(A::sub(U.y, U.x), k.idx), A::mul(A::sub(V.y, VS.y), k.idy)));
+      st2(f + c, fa, fb);
+      a = fmax(fabs(fa), fabs(fb));
+      sum = fa + fb;
+    } else {
+      f[c] = fa;
+      a = fabs(fa);
+      sum = fa;
+    }
+  }
+  const double m = block_max(a, sh);
+  if (threadIdx.x == 0 && threadIdx.y == 0) atomic_max_nonneg(&st->maxf_bits, m);
+  if (partial) {
+    const double s = block_sum(sum, sh);
     if (threadIdx.x == 0 && threadIdx.y == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
   }
 }
@@ -431,6 +503,43 @@ __global__ void __launch_bounds__(PM_BX* PM_BY)
   if (j <= k.ny - 1) {
     const bool valid = (j == k.ny - 1) || fl_c || fl_n;
     v[c] = valid ? A::sub(vs[c], A::mul(k.cv, A::sub(p[pn_i], pc))) : 0.0;
+  }
+}
+
+// Row version for the unmasked cases (see k_predict_rows).  psplit: p is the final buffer of the tiled solve in
+// its split-row layout, where the pair (i, i+1) is one double in each half of the row.
+template <class A>
+__global__ void __launch_bounds__(PM_RX* PM_RY)
+    k_correct_rows(const __grid_constant__ KP k, const double* __restrict__ us, const double* __restrict__ vs,
+                   const double* __restrict__ p, double* __restrict__ u, double* __restrict__ v, int psplit) {
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x) + 1;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > k.nx || jl > k.nyl) return;
+  const int j = k.j0 + jl, P = k.pitch;
+  const size_t c = pm_idx(k, jl, i);
+  double pa, pb, pe2, pna, pnb;
+  if (psplit) {
+    const size_t sa = pm_sidx(k, jl, i), sb = pm_sidx(k, jl, i + 1);
+    pa = p[sa]; pb = p[sb]; pe2 = p[pm_sidx(k, jl, i + 2)];
+    pna = p[sa + P]; pnb = p[sb + P];
+  } else {
+    const double2 Pc = ld2(p + c), Pn = ld2(p + c + P);
+    pa = Pc.x; pb = Pc.y; pe2 = p[c + 2];
+    pna = Pn.x; pnb = Pn.y;
+  }
+  const bool a_u = i <= k.nx - 1, b_u = i + 1 <= k.nx - 1;
+  const bool a_v = j <= k.ny - 1, b_v = a_v && i + 1 <= k.nx;
+  if (a_u) {
+    const double2 U = ld2(us + c);
+    const double ua = A::sub(U.x, A::mul(k.cu, A::sub(pb, pa)));
+    if (b_u) st2(u + c, ua, A::sub(U.y, A::mul(k.cu, A::sub(pe2, pb))));
+    else u[c] = ua;
+  }
+  if (a_v) {
+    const double2 V = ld2(vs + c);
+    const double va = A::sub(V.x, A::mul(k.cv, A::sub(pna, pa)));
+    if (b_v) st2(v + c, va, A::sub(V.y, A::mul(k.cv, A::sub(pnb, pb))));
+    else v[c] = va;
   }
 }
 
