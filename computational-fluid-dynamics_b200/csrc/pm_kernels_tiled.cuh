@@ -31,31 +31,38 @@
 
 #include "pm_common.cuh"
 
+// Tile shape.  Red-black: 4 segments x 12 rows = 48 x 128 cells on 256 threads -- eight warps per CTA spread evenly
+// over the four SM sub-partitions (ten did not: 3/3/2/2), and the taller tile raises the share of output cells from
+// 63 % to 68 % at T = 3; it costs the full 128 registers per thread (96 hold the thread's 24 cells of p and f).
+// Jacobi stages a whole sweep of new values in registers and keeps 5 segments x 8 rows on 320 threads.
 #ifndef PM_TILE_NSEG
-#define PM_TILE_NSEG 5   // row segments per tile; 64 threads (column pairs) each
+#define PM_TILE_NSEG 4   // row segments per tile; 64 threads (column pairs) each
 #endif
 #ifndef PM_TILE_RPT
-#define PM_TILE_RPT 8    // rows per thread (even: keeps the colour of a thread's first row uniform over the launch)
+#define PM_TILE_RPT 12   // rows per thread (even: keeps the colour of a thread's first row uniform over the launch)
+#endif
+#ifndef PM_TILE_NSEG_JACOBI
+#define PM_TILE_NSEG_JACOBI 5
+#endif
+#ifndef PM_TILE_RPT_JACOBI
+#define PM_TILE_RPT_JACOBI 8
 #endif
 #ifndef PM_TILE_MINBLOCKS
 #define PM_TILE_MINBLOCKS 2
 #endif
-#ifndef PM_TILE_F_SMEM
-#define PM_TILE_F_SMEM 0  // 1: f lives in shared memory (thread-private, conflict-free layout) instead of registers
-#endif
-#define PM_TILE_THREADS (64 * PM_TILE_NSEG)
 
 template <int METHOD, int T>
 struct TileCfg {
   static constexpr int H = (METHOD == PM_PPE_SOR_RB) ? 2 * T : ((T + 1) / 2) * 2;  // even: keeps 16-byte alignment of row pairs
   static constexpr int SW = 128;                  // tile width in doubles == 64 column pairs == one TMA box row (1 KiB)
-  static constexpr int NSEG = PM_TILE_THREADS / 64;
-  static constexpr int RPT = PM_TILE_RPT;         // rows per thread
+  static constexpr int NSEG = (METHOD == PM_PPE_SOR_RB) ? PM_TILE_NSEG : PM_TILE_NSEG_JACOBI;
+  static constexpr int RPT = (METHOD == PM_PPE_SOR_RB) ? PM_TILE_RPT : PM_TILE_RPT_JACOBI;  // rows per thread
+  static constexpr int THREADS = 64 * NSEG;
+  static constexpr int NWARPS = THREADS / 32;
   static constexpr int SH = NSEG * RPT;           // tile height
   static constexpr int TX = SW - 2 * H;           // output block
   static constexpr int TY = SH - 2 * H;
-  static constexpr int F_BYTES = PM_TILE_F_SMEM ? 2 * RPT * PM_TILE_THREADS * 8 : 0;
-  static constexpr int SMEM_BYTES = (SH + 2) * SW * 8 + F_BYTES;  // tile + one spare row above and below (+ f)
+  static constexpr int SMEM_BYTES = (SH + 2) * SW * 8;  // tile + one spare row above and below
   static_assert(TX > 0 && TY > 0, "halo too deep for the tile");
   static_assert(RPT % 2 == 0 && TY % 2 == 0, "PAR0 (colour of a thread's first row) must not depend on the segment or the tile row");
   static_assert(H <= PM_PADR, "halo deeper than the pad rows of the planes");
@@ -160,19 +167,13 @@ __device__ __forceinline__ double cell_residual(const KP& k, int j, int i, doubl
   return res_channel<A>(k, pc, pe, pw, pn, ps, f);
 }
 
-// Per-thread view of the tile.
+// Per-thread view of the tile: RPT rows x 2 columns of p and f in registers for the whole pass.
 template <int RPT>
 struct Cells {
   double p0[RPT], p1[RPT];
-#if PM_TILE_F_SMEM
-  const double* fs;  // this thread's slot of the f block: value (r, xy) at fs[(2 * r + xy) * PM_TILE_THREADS]
-  __device__ __forceinline__ double f0v(int r) const { return fs[(2 * r) * PM_TILE_THREADS]; }
-  __device__ __forceinline__ double f1v(int r) const { return fs[(2 * r + 1) * PM_TILE_THREADS]; }
-#else
   double f0[RPT], f1[RPT];
   __device__ __forceinline__ double f0v(int r) const { return f0[r]; }
   __device__ __forceinline__ double f1v(int r) const { return f1[r]; }
-#endif
 };
 
 // m = max(m, |x|) where `on`, with the semantics of std::max(m, std::abs(x)) (a NaN never replaces m).
@@ -536,24 +537,18 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
   // Every updatable cell of the tile strictly inside the domain (uniform over the block)?
   const bool interior = ib + 1 >= 2 && ib + SW - 2 <= k.nx - 1 && k.j0 + jb + 1 >= 2 && k.j0 + jb + SH - 2 <= k.ny - 1 &&
                         jb + SH - 1 <= k.nyl + H;
-  if (tid < (PM_TILE_THREADS / 32) * (T + 1)) red[tid] = 0ull;  // ordered before the warps' stores by the barriers below
+  if (tid < C::NWARPS * (T + 1)) red[tid] = 0ull;  // ordered before the warps' stores by the barriers below
 
-  // f: HBM -> registers (or the thread's private shared-memory slots), 128-bit row loads, overlapping the TMA transfer of p
+  // f: HBM -> registers, 128-bit row loads, overlapping the TMA transfer of p
   Cells<RPT> c;
-#if PM_TILE_F_SMEM
-  double* fsw = tile + (SH + 1) * SW + tid;  // behind the tile and its spare row
-  c.fs = fsw;
-#define PM_PUT_F(r, vx, vy) do { fsw[(2 * (r)) * PM_TILE_THREADS] = (vx); fsw[(2 * (r) + 1) * PM_TILE_THREADS] = (vy); } while (0)
-#else
-#define PM_PUT_F(r, vx, vy) do { c.f0[r] = (vx); c.f1[r] = (vy); } while (0)
-#endif
   {
     const double* fp = f + pm_idx(k, jl0, i0);
     if (interior) {
 #pragma unroll
       for (int r = 0; r < RPT; ++r) {
         const double2 v = __ldg(reinterpret_cast<const double2*>(fp + size_t(r) * k.pitch));
-        PM_PUT_F(r, v.x, v.y);
+        c.f0[r] = v.x;
+        c.f1[r] = v.y;
       }
     } else {
 #pragma unroll
@@ -563,11 +558,11 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
         if (rowI && colI0 && colI1) v = __ldg(reinterpret_cast<const double2*>(fp + size_t(r) * k.pitch));
         else if (rowI && colI0) v.x = __ldg(fp + size_t(r) * k.pitch);
         else if (rowI && colI1) v.y = __ldg(fp + size_t(r) * k.pitch + 1);
-        PM_PUT_F(r, v.x, v.y);
+        c.f0[r] = v.x;
+        c.f1[r] = v.y;
       }
     }
   }
-#undef PM_PUT_F
   PM_PROF(0);  // masks, f loads issued
   if (check_stop) {  // the reference's loop test (uniform over the grid); the tile loads above are already in flight
     int first;
@@ -632,7 +627,7 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
     // iterate m0+t (before sweep t+1 replaces it) and the colour-1 part taken right after sweep t created it.
     unsigned long long v = 0ull;
 #pragma unroll
-    for (int w = 0; w < PM_TILE_THREADS / 32; ++w) v = max(v, red[w * (T + 1) + tid]);
+    for (int w = 0; w < C::NWARPS; ++w) v = max(v, red[w * (T + 1) + tid]);
     unsigned long long* mine = fold_part + size_t((blockIdx.y * gridDim.x + blockIdx.x) & (PM_FOLD_SLOTS - 1)) * 16;
     if (v != 0ull && m >= 1 && m <= k.max_iters) atomicMax(&mine[m & 7], v);
   }
@@ -644,7 +639,7 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
 
 // One tile per CTA, two CTAs per SM: one CTA's loads overlap the other's sweeps.
 template <class A, int FORM, int METHOD, int T, int PAR0>
-__global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
+__global__ void __launch_bounds__((TileCfg<METHOD, T>::THREADS), PM_TILE_MINBLOCKS)
     k_ppe_tiled(const __grid_constant__ KP k, const __grid_constant__ CUtensorMap tmap_in, double* __restrict__ pout,
                 const double* __restrict__ f, PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits,
                 unsigned long long* __restrict__ fold_part, int m0, int nsw, int force, int tile_row0) {
@@ -652,7 +647,7 @@ __global__ void __launch_bounds__(PM_TILE_THREADS, PM_TILE_MINBLOCKS)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   double* tile = reinterpret_cast<double*>(smem_raw) + C::SW;  // one spare row above (and one below)
   __shared__ __align__(8) uint64_t mbar;
-  __shared__ unsigned long long red[(PM_TILE_THREADS / 32) * (T + 1)];  // per warp: bit patterns of the residual maxima of iterates m0 .. m0+T
+  __shared__ unsigned long long red[C::NWARPS * (T + 1)];  // per warp: bit patterns of the residual maxima of iterates m0 .. m0+T
 
   const int tid = threadIdx.x;
   // tile rows rotated by one: the last row of the launch (all boundary tiles at the top wall, several times
@@ -704,6 +699,7 @@ struct TiledPlan {
   int sweeps = 1;       // T
   int halo = 2;         // H
   int tx = 0, ty = 0;   // output block
+  int sh = 0, threads = 0;  // tile rows, threads per CTA
   int tiles_x = 0, tiles_y = 0;
   int smem_bytes = 0;
   int psh = 0;          // column shift of the split-row layout (KP::psh)
@@ -733,7 +729,8 @@ static const void* tiled_kernel_ptr(int par0) {
 template <int METHOD, int T>
 static void tiled_geometry(TiledPlan* pl) {
   using C = TileCfg<METHOD, T>;
-  pl->sweeps = T; pl->halo = C::H; pl->tx = C::TX; pl->ty = C::TY; pl->smem_bytes = C::SMEM_BYTES; pl->psh = C::PSH;
+  pl->sweeps = T; pl->halo = C::H; pl->tx = C::TX; pl->ty = C::TY; pl->sh = C::SH; pl->threads = C::THREADS;
+  pl->smem_bytes = C::SMEM_BYTES; pl->psh = C::PSH;
 }
 
 template <class A, int FORM>
@@ -775,7 +772,7 @@ static inline bool tiled_create(TiledPlan* pl, const pm_config& c, const KP& k, 
   for (int b = 0; b < 2; ++b) {  // {pair, parity, row} view of a split-row plane
     const cuuint64_t gdim[3] = {cuuint64_t(k.pitch / 2), 2u, cuuint64_t(rows_alloc)};
     const cuuint64_t gstr[2] = {cuuint64_t(k.pitch / 2) * 8, cuuint64_t(k.pitch) * 8};
-    const cuuint32_t box[3] = {64u, 2u, cuuint32_t(TileCfg<0, 1>::SH)};
+    const cuuint32_t box[3] = {64u, 2u, cuuint32_t(pl->sh)};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = encode(&pl->map[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, pl->p[b], gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -803,7 +800,7 @@ static inline cudaError_t tiled_launch(const TiledPlan* pl, const KP& k, int in,
   double* pout = pl->p[in ^ 1];
   void* args[] = {(void*)&k, (void*)&pl->map[in], (void*)&pout, (void*)&f, (void*)&st, (void*)&res, (void*)&pl->fold_part,
                   (void*)&m0, (void*)&nsw, (void*)&force, (void*)&tile_row0};
-  return cudaLaunchKernel(pl->kernel, dim3(pl->tiles_x, tile_rows), dim3(PM_TILE_THREADS), args, size_t(pl->smem_bytes), stream);
+  return cudaLaunchKernel(pl->kernel, dim3(pl->tiles_x, tile_rows), dim3(pl->threads), args, size_t(pl->smem_bytes), stream);
 }
 // Behind all launches of the pass that started at iterate m0 with nsw sweeps.
 static inline cudaError_t tiled_fold_launch(const TiledPlan* pl, const KP& k, unsigned long long* res, int m0, int nsw, cudaStream_t stream) {
