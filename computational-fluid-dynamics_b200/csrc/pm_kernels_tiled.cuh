@@ -740,6 +740,7 @@ static const void* tiled_pick(int method, int T, int par0, TiledPlan* pl) {
       case 1: tiled_geometry<PM_PPE_SOR_RB, 1>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 1>(par0);
       case 2: tiled_geometry<PM_PPE_SOR_RB, 2>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 2>(par0);
       case 3: tiled_geometry<PM_PPE_SOR_RB, 3>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 3>(par0);
+      case 4: tiled_geometry<PM_PPE_SOR_RB, 4>(pl); return tiled_kernel_ptr<A, FORM, PM_PPE_SOR_RB, 4>(par0);
     }
   } else {
     switch (T) {
@@ -752,13 +753,13 @@ static const void* tiled_pick(int method, int T, int par0, TiledPlan* pl) {
 }
 
 static inline bool tiled_create(TiledPlan* pl, const pm_config& c, const KP& k, double* p0, double* p1, int rows_alloc, std::string* err) {
-  int T = c.sweeps_per_pass > 0 ? c.sweeps_per_pass : (c.ppe_method == PM_PPE_SOR_RB ? 3 : 2);
+  int T = c.sweeps_per_pass > 0 ? c.sweeps_per_pass : (c.ppe_method == PM_PPE_SOR_RB ? 4 : 2);
   const bool cav = c.case_id == PM_CASE_CAVITY;
   const void* kern = nullptr;
   const int par0 = k.j0 & 1;
   if (c.exact_arith) kern = cav ? tiled_pick<Exact, 0>(c.ppe_method, T, par0, pl) : tiled_pick<Exact, 1>(c.ppe_method, T, par0, pl);
   else kern = cav ? tiled_pick<Fast, 0>(c.ppe_method, T, par0, pl) : tiled_pick<Fast, 1>(c.ppe_method, T, par0, pl);
-  if (!kern) { *err = "sweeps_per_pass " + std::to_string(T) + " not built for this method (red-black: 1,2,3; jacobi: 1,2,4)"; return false; }
+  if (!kern) { *err = "sweeps_per_pass " + std::to_string(T) + " not built for this method (red-black: 1,2,3,4; jacobi: 1,2,4)"; return false; }
   pl->kernel = kern;
   pl->tiles_x = (k.nx + pl->tx - 1) / pl->tx;
   pl->tiles_y = (k.nyl + pl->ty - 1) / pl->ty;

@@ -201,8 +201,8 @@ def test_large_grid_jacobi_bit_exact(pm, orc, nx, ny):
 
 TILED_CASES = [
     # case, nx, ny, method, T
-    (0, 48, 48, RB, 1), (0, 48, 48, RB, 2), (0, 250, 131, RB, 2), (0, 250, 131, RB, 3), (0, 117, 61, RB, 3),
-    (1, 93, 31, RB, 1), (1, 93, 31, RB, 2), (1, 300, 70, RB, 2), (1, 300, 70, RB, 3), (1, 121, 77, RB, 3),
+    (0, 48, 48, RB, 1), (0, 48, 48, RB, 2), (0, 250, 131, RB, 2), (0, 250, 131, RB, 3), (0, 117, 61, RB, 3), (0, 250, 131, RB, 4), (0, 117, 61, RB, 4),
+    (1, 93, 31, RB, 1), (1, 93, 31, RB, 2), (1, 300, 70, RB, 2), (1, 300, 70, RB, 3), (1, 121, 77, RB, 3), (1, 300, 70, RB, 4),
     (0, 48, 48, JAC, 1), (0, 250, 131, JAC, 2), (0, 250, 131, JAC, 4), (1, 93, 31, JAC, 1), (1, 300, 70, JAC, 2), (1, 300, 70, JAC, 4),
 ]
 
@@ -222,7 +222,7 @@ def test_tiled_ppe_bit_exact(pm, orc, case_id, nx, ny, method, T, K):
     assert_fields_equal(S, O, (2,), "tiled ppe")
 
 
-@pytest.mark.parametrize("case_id,nx,ny,method,T", [(0, 400, 300, RB, 3), (0, 400, 300, RB, 2), (1, 384, 200, RB, 3), (0, 400, 300, JAC, 2),
+@pytest.mark.parametrize("case_id,nx,ny,method,T", [(0, 400, 300, RB, 3), (0, 400, 300, RB, 2), (0, 400, 300, RB, 4), (1, 384, 200, RB, 3), (1, 384, 200, RB, 4), (0, 400, 300, JAC, 2),
                                                    (1, 384, 200, JAC, 4)])
 def test_tiled_production_arithmetic_close_to_oracle(pm, orc, case_id, nx, ny, method, T):
     """Production arithmetic on the tiled path, grids with interior tiles (the residual-form relaxation with
@@ -239,7 +239,7 @@ def test_tiled_production_arithmetic_close_to_oracle(pm, orc, case_id, nx, ny, m
     assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(b).max()), f"p off by {np.abs(a - b).max():.3e} vs scale {np.abs(b).max():.3e}"
 
 
-@pytest.mark.parametrize("case_id,nx,ny,T,steps", [(0, 40, 40, 2, 4), (0, 40, 40, 3, 4), (1, 93, 31, 2, 2), (1, 93, 31, 3, 2)])
+@pytest.mark.parametrize("case_id,nx,ny,T,steps", [(0, 40, 40, 2, 4), (0, 40, 40, 3, 4), (0, 40, 40, 4, 4), (1, 93, 31, 2, 2), (1, 93, 31, 3, 2), (1, 93, 31, 4, 2)])
 def test_tiled_stopping_rule_bit_exact(pm, orc, case_id, nx, ny, T, steps):
     """Run to the reference tolerance through the tiled path: the device-side loop test plus the
     partial replay pass must land on exactly the iterate the oracle stops at."""
@@ -260,7 +260,7 @@ def test_large_grid_8192_tiled_equals_general_path(pm, exact):
     arithmetic the two agree to 1e-12 relative."""
     n = 8192
     out = []
-    for path, T in ((1, 0), (2, 2), (2, 3)):
+    for path, T in ((1, 0), (2, 2), (2, 3), (2, 4)):
         cfg = make_cfg(pm, 0, n, n, RB, exact, 9, path=path)
         cfg.sweeps_per_pass = T
         cfg.tol_factor = 1e-12  # at h = 1/8192 max|f| >= 2 nu U / h^3 = 1.1e9 and the reference's 1e-9 would skip the loop
