@@ -280,9 +280,9 @@ def run_ours(args):
                 S.host_step_run()
             S.host_step_drain()
 
-        s_steps = max(1, min(args.steps, 2))
+        s_steps = max(1, min(args.steps, 2 if world == 1 else 1))
         s_ms = wall_ms(serial, s_steps)
-        e_steps = max(2, min(args.steps, 20))
+        e_steps = max(2, min(args.steps, 20 if world == 1 else 8))  # 16384^2 slabs move 4x the bytes per step
         streamed(2)  # first use allocates the extra plane sets
         e_ms = wall_ms(streamed, e_steps)
         e2e = {"value": cells * e_steps / (e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
