@@ -30,48 +30,7 @@
 #include <string>
 
 #include "pm_common.cuh"
-
-// Tile shape.  Red-black: 4 segments x 12 rows = 48 x 128 cells on 256 threads -- eight warps per CTA spread evenly
-// over the four SM sub-partitions (ten did not: 3/3/2/2), and the taller tile raises the share of output cells from
-// 63 % to 68 % at T = 3; it costs the full 128 registers per thread (96 hold the thread's 24 cells of p and f).
-// Jacobi stages a whole sweep of new values in registers and keeps 5 segments x 8 rows on 320 threads.
-#ifndef PM_TILE_NSEG
-#define PM_TILE_NSEG 4   // row segments per tile; 64 threads (column pairs) each
-#endif
-#ifndef PM_TILE_RPT
-#define PM_TILE_RPT 12   // rows per thread (even: keeps the colour of a thread's first row uniform over the launch)
-#endif
-#ifndef PM_TILE_NSEG_JACOBI
-#define PM_TILE_NSEG_JACOBI 5
-#endif
-#ifndef PM_TILE_RPT_JACOBI
-#define PM_TILE_RPT_JACOBI 8
-#endif
-#ifndef PM_TILE_MINBLOCKS
-#define PM_TILE_MINBLOCKS 2
-#endif
-
-template <int METHOD, int T>
-struct TileCfg {
-  static constexpr int H = (METHOD == PM_PPE_SOR_RB) ? 2 * T : ((T + 1) / 2) * 2;  // even: keeps 16-byte alignment of row pairs
-  static constexpr int SW = 128;                  // tile width in doubles == 64 column pairs == one TMA box row (1 KiB)
-  static constexpr int NSEG = (METHOD == PM_PPE_SOR_RB) ? PM_TILE_NSEG : PM_TILE_NSEG_JACOBI;
-  static constexpr int RPT = (METHOD == PM_PPE_SOR_RB) ? PM_TILE_RPT : PM_TILE_RPT_JACOBI;  // rows per thread
-  static constexpr int THREADS = 64 * NSEG;
-  static constexpr int NWARPS = THREADS / 32;
-  static constexpr int SH = NSEG * RPT;           // tile height
-  static constexpr int TX = SW - 2 * H;           // output block
-  static constexpr int TY = SH - 2 * H;
-  static constexpr int SMEM_BYTES = (SH + 2) * SW * 8;  // tile + one spare row above and below
-  static_assert(TX > 0 && TY > 0, "halo too deep for the tile");
-  static_assert(RPT % 2 == 0 && TY % 2 == 0, "PAR0 (colour of a thread's first row) must not depend on the segment or the tile row");
-  static_assert(H <= PM_PADR, "halo deeper than the pad rows of the planes");
-  static_assert(H % 2 == 0 && TX % 4 == 0 && (PM_OFFC + 1) % 2 == 0 && PM_OFFC + 1 >= H,
-                "the first storage column of every tile must be even (it is the .x cell of lane 0), non-negative, and the same mod 4 for all tiles");
-  // shift of the split-row layout that makes (first storage column + PSH) / 2 even: 16-byte aligned TMA box rows
-  static constexpr int PSH = (4 - ((PM_OFFC + 1 - H) & 3)) & 3;
-  static_assert(PSH == 0 || PSH == 2, "");
-};
+#include "pm_tile_cfg.cuh"
 
 // ---- mbarrier / TMA primitives (sm_90+ PTX; SASS: SYNCS.*, UTMALDG) -----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

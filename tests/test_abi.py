@@ -106,3 +106,18 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "Mcell-updates/s per projection step" and d["unit"] == "Mcell-updates/s"
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["higher_is_better"] is True
+
+
+def test_split_row_layout_properties(tmp_path):
+    """The split-row layout of the tiled solve (pm_split_col, TileCfg::PSH): bijection per row, even/odd halves, and a
+    16-byte aligned, in-range TMA box start for every tile of every tile shape.  Host-only program built with nvcc."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = tmp_path / "split_check"
+    src = os.path.join(ROOT, "tests", "helpers", "split_layout_check.cu")
+    subprocess.run([nvcc, "-std=c++17", "-o", str(exe), src], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "split layout ok" in out.stdout, out.stdout + out.stderr
