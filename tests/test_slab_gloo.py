@@ -127,7 +127,7 @@ def _ghosts(O, p, nx, ny, a, b, rank, world):
 
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("case_id,nx,ny", [(0, 20, 26), (1, 30, 23)])
-@pytest.mark.parametrize("mode,T", [("general", 1), ("tiled", 2), ("tiled", 3)])
+@pytest.mark.parametrize("mode,T", [("general", 1), ("tiled", 2), ("tiled", 3), ("tiled", 4)])
 def test_slabs_equal_single_domain(tmp_path, world, case_id, nx, ny, mode, T):
     orc, _ = _setup()
     K = 7
