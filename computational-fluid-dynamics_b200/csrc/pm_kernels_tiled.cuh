@@ -17,8 +17,11 @@
 //   * residuals cost no extra loads: a Jacobi or red update reads exactly the operands of the
 //     residual of the iterate it replaces; a black update's operands are the residual operands of
 //     the iterate it creates (reference residual trees: cavity-01.cpp:664-673, channel-01.cpp:676-678);
-//   * the output block is written with 128-bit stores; wall ghosts (channel form) are refreshed by
-//     the thread that owns the wall-adjacent cell, in the tile and in HBM (channel-01.cpp:531-541).
+//   * the output block is written in the split-row layout (consecutive lanes to consecutive doubles of either
+//     half of the row); wall ghosts (channel form) are refreshed by the thread that owns the wall-adjacent
+//     cell, in the tile and in HBM (channel-01.cpp:531-541);
+//   * per-iterate residual maxima: per-warp shared slots -> one global atomicMax per iterate and tile into one of
+//     32 slot lines -> k_tiled_fold behind the pass.
 // The reference's loop test (cavity-01.cpp:635) is evaluated on the device at the start of every
 // pass from the residuals of the previous pass; passes after convergence exit at once and leave
 // both buffers untouched, and the host re-runs at most one partial pass to land on the exact iterate.
@@ -459,7 +462,7 @@ __global__ void k_tiled_fold(unsigned long long* __restrict__ part, unsigned lon
 }
 
 // Everything one CTA does for one tile once its TMA load has been issued on `bar`: masks, f loads, wait,
-// split-row rewrite, the sweeps, the 128-bit write-out and the per-iterate residual atomics.
+// the sweeps, the write-out and the per-iterate residual atomics.
 template <class A, int FORM, int METHOD, int T, int PAR0>
 __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t* bar, uint32_t phase, unsigned long long* red,
                                              double* __restrict__ pout, const double* __restrict__ f, PpeState* __restrict__ st,

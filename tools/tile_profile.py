@@ -24,7 +24,7 @@ S.step(2)
 ms = S.timer_stop()
 pm.lib().pm_debug_tile_profile(buf, 0)
 ctas = buf[7]
-names = ["masks + f loads issued", "wait for the TMA tile", "own cells (+f arrival) + split-row rewrite", "sweeps", "write-out + residual atomics"]
+names = ["masks + f loads issued", "wait for the TMA tile", "own cells out of the tile", "sweeps", "write-out + residual atomics"]
 names.append("kernel entry: mbarrier, TMA issue, loop-test loads, barrier")
 tot = sum(buf[q] for q in range(6))
 print(f"{n}x{n}: {ms / 2:.2f} ms/step, {ctas} tile CTAs, {tot / ctas:.0f} cycles per CTA")
