@@ -668,6 +668,25 @@ extern "C" int pm_source(pm_solver* s) {
   return PM_OK;
 }
 
+// Cavity: predictor and source in one pass (k_predict_source_cavity); what pm_predict followed by pm_source does.
+static int predict_source_fused(pm_solver* s) {
+  CK(cudaSetDevice(s->device));
+  const KP& k = s->kp;
+  PMTRY(exchange_halo1(s, s->pl[PL_U]));
+  PMTRY(exchange_halo(s, s->pl[PL_V], 2, s->stream));  // the row below the slab is recomputed: it reads v two rows down
+  CK(cudaMemsetAsync(&s->d_state->maxf_bits, 0, 2 * sizeof(unsigned long long), s->stream));
+  const dim3 g(((k.nx + 1) / 2 + PM_RX - 1) / PM_RX, (k.nyl + PM_FUSE_ROWS - 1) / PM_FUSE_ROWS);
+  if (s->cfg.exact_arith)
+    k_predict_source_cavity<Exact><<<g, PM_RX, 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->pl[PL_US], s->pl[PL_VS], s->pl[PL_F], s->d_state);
+  else
+    k_predict_source_cavity<Fast><<<g, PM_RX, 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->pl[PL_US], s->pl[PL_VS], s->pl[PL_F], s->d_state);
+  CKL(s);
+  // the tolerance rule reads max|f| of this very pass (cavity-01.cpp:628-632)
+  PMTRY(publish_words(s, &s->d_state->maxf2_bits, &s->d_state->maxf_bits, sizeof(unsigned long long)));
+  s->f_max_valid = true;
+  return PM_OK;
+}
+
 extern "C" int pm_correct(pm_solver* s) {
   if (!s) return PM_ERR_INVALID_ARGUMENT;
   CK(cudaSetDevice(s->device));
@@ -1106,8 +1125,12 @@ extern "C" int pm_step(pm_solver* s, int nsteps, pm_ppe_result* last) {
   for (int n = 0; n < nsteps; ++n) {
     if (s->kp.case_id == PM_CASE_CAVITY) {  // cavity-01.cpp:387-390
       PMTRY(pm_apply_bc(s, 0));
-      PMTRY(pm_predict(s));
-      PMTRY(pm_source(s));
+      if (s->cfg.nranks == 1 || s->kp.nyl >= 2) {
+        PMTRY(predict_source_fused(s));
+      } else {
+        PMTRY(pm_predict(s));
+        PMTRY(pm_source(s));
+      }
       PMTRY(pm_ppe_solve(s, &r));
       PMTRY(pm_correct(s));
     } else {  // channel-01.cpp:368-375

@@ -245,6 +245,96 @@ __global__ void __launch_bounds__(PM_RX* PM_RY)
   }
 }
 
+// Predictor + source in one pass for the cavity, where nothing happens between the two (cavity-01.cpp:388-389 and
+// :622-630; channel/step apply boundary conditions to u*, v* in between): u*, v* are written as k_predict_rows writes
+// them and f is formed from the values still in registers, so u*, v* are not read back (16 B per cell less).
+// A thread owns the columns i, i+1 (i odd) of PM_FUSE_ROWS consecutive rows: v* of the row below stays in registers,
+// u* of the column to the west comes through shared memory (the first thread of a block recomputes it), and the
+// row below the strip is recomputed once per strip.  Boundary faces the predictor never writes (u*[j][0], u*[j][nx],
+// v*[0][i], v*[ny][i]) are read from memory, exactly as the separate source pass would see them.
+#define PM_FUSE_ROWS 16
+template <class A>
+__global__ void __launch_bounds__(PM_RX)
+    k_predict_source_cavity(const __grid_constant__ KP k, const double* __restrict__ u, const double* __restrict__ v,
+                            double* __restrict__ us, double* __restrict__ vs, double* __restrict__ f, PpeState* __restrict__ st) {
+  __shared__ double s_ub[2][PM_RX];
+  __shared__ double sh[32];
+  const int tid = threadIdx.x;
+  const int i = 2 * (blockIdx.x * blockDim.x + tid) + 1;
+  const int jl0 = blockIdx.y * PM_FUSE_ROWS + 1;
+  const int P = k.pitch;
+  const bool has = i <= k.nx, has_b = i + 1 <= k.nx;
+  const bool a_u = i <= k.nx - 1, b_u = i + 1 <= k.nx - 1;  // columns whose u* the predictor writes
+  double a_max = 0.0;
+  double va_prev = 0.0, vb_prev = 0.0;  // v* of the row below the current one
+  if (has) {
+    const int jl = jl0 - 1, j = k.j0 + jl;
+    const size_t c = pm_idx(k, jl, i);
+    if (j == 0) {  // bottom wall faces: never written by the predictor
+      const double2 Vm = ld2(vs + c);
+      va_prev = Vm.x; vb_prev = Vm.y;
+    } else {       // last row of the strip below (another block writes it): same trees, same operands
+      const double2 U = ld2(u + c), UN = ld2(u + c + P);
+      const double2 V = ld2(v + c), VN = ld2(v + c + P), VS = ld2(v + c - P);
+      const double uW = u[c - 1], uNW = u[c + P - 1], vW = v[c - 1], vE2 = v[c + 2];
+      va_prev = pred_v<A>(k, V.x, V.y, vW, VN.x, VS.x, U.x, UN.x, uW, uNW);
+      vb_prev = pred_v<A>(k, V.y, vE2, V.x, VN.y, VS.y, U.y, UN.y, U.x, UN.x);
+    }
+  }
+  for (int r = 0; r < PM_FUSE_ROWS; ++r) {
+    const int jl = jl0 + r;
+    if (jl > k.nyl) break;  // uniform over the block
+    const int j = k.j0 + jl;
+    const size_t c = pm_idx(k, jl, i);
+    double ua = 0.0, ub = 0.0, va = 0.0, vb = 0.0, uw = 0.0;
+    if (has) {
+      const double2 U = ld2(u + c), UN = ld2(u + c + P), US = ld2(u + c - P);
+      const double2 V = ld2(v + c), VN = ld2(v + c + P), VS = ld2(v + c - P);
+      const double uW = u[c - 1], uE2 = u[c + 2], uNW = u[c + P - 1];
+      const double vW = v[c - 1], vE2 = v[c + 2], vSE2 = v[c - P + 2];
+      const bool a_v = j <= k.ny - 1;
+      // u*: computed where the predictor writes, memory elsewhere (east wall face of the last column)
+      if (a_u) ua = pred_u<A>(k, U.x, uW, U.y, UN.x, US.x, V.x, V.y, VS.x, VS.y);
+      else ua = us[c];
+      if (b_u) ub = pred_u<A>(k, U.y, U.x, uE2, UN.y, US.y, V.y, vE2, VS.y, vSE2);
+      else if (has_b) ub = us[c + 1];
+      if (a_u && b_u) st2(us + c, ua, ub);
+      else if (a_u) us[c] = ua;
+      if (a_v) {
+        va = pred_v<A>(k, V.x, V.y, vW, VN.x, VS.x, U.x, UN.x, uW, uNW);
+        vb = pred_v<A>(k, V.y, vE2, V.x, VN.y, VS.y, U.y, UN.y, U.x, UN.x);
+        if (has_b) st2(vs + c, va, vb);
+        else vs[c] = va;
+      } else {  // top wall faces
+        const double2 Vm = ld2(vs + c);
+        va = Vm.x; vb = Vm.y;
+      }
+      if (tid == 0) {  // u* of the column to the west of the block
+        if (i == 1) uw = us[c - 1];  // west wall face
+        else uw = pred_u<A>(k, uW, u[c - 2], U.x, uNW, u[c - P - 1], vW, V.x, v[c - P - 1], VS.x);
+      }
+    }
+    s_ub[r & 1][tid] = ub;
+    __syncthreads();
+    if (has) {
+      if (tid > 0) uw = s_ub[r & 1][tid - 1];
+      const double fa = A::mul(k.src_coef, A::add(A::mul(A::sub(ua, uw), k.idx), A::mul(A::sub(va, va_prev), k.idy)));
+      if (has_b) {
+        const double fb = A::mul(k.src_coef, A::add(A::mul(A::sub(ub, ua), k.idx), A::mul(A::sub(vb, vb_prev), k.idy)));
+        st2(f + c, fa, fb);
+        a_max = fmax(a_max, fmax(fabs(fa), fabs(fb)));
+      } else {
+        f[c] = fa;
+        a_max = fmax(a_max, fabs(fa));
+      }
+      va_prev = va;
+      vb_prev = vb;
+    }
+  }
+  const double m = block_max(a_max, sh);
+  if (tid == 0) atomic_max_nonneg(&st->maxf_bits, m);
+}
+
 // k5 (fast policy): fixed-shape tree over the per-block partial sums, one block.
 __global__ void k_mean_from_partials(const double* __restrict__ partial, int n, int count, PpeState* __restrict__ st) {
   __shared__ double sh[32];
