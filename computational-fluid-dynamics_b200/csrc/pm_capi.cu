@@ -44,7 +44,9 @@ struct pm_solver {
   KP kp{};
   int device = 0;
   cudaStream_t stream = nullptr, comm_stream = nullptr;
-  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_halo = nullptr, ev_edge = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_halo = nullptr, ev_edge = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
+  bool step_timed = false;
+  double last_step_ppe_ms = 0.0;
   size_t plane = 0;        // doubles per plane
   int rows_alloc = 0;
   double* base = nullptr;  // PL_COUNT planes
@@ -59,7 +61,8 @@ struct pm_solver {
   PpeState* d_state = nullptr;
   unsigned long long* d_res = nullptr;  // max_iters + 2 entries
   double* d_partial = nullptr;
-  int n_partial = 0;
+  int n_partial = 0;    // blocks of cell_grid (k_source, k_diag)
+  int cap_partial = 0;  // allocated slots: max over the grids that write partial sums
   PpeState* h_state = nullptr;  // pinned
   unsigned long long* h_res = nullptr;  // pinned, max_iters + 2
   bool f_max_valid = false;
@@ -243,7 +246,7 @@ static int destroy_impl(pm_solver* s) {
   if (s->d_partial) cudaFree(s->d_partial);
   if (s->h_state) cudaFreeHost(s->h_state);
   if (s->h_res) cudaFreeHost(s->h_res);
-  for (cudaEvent_t e : {s->ev_a, s->ev_b, s->ev_t0, s->ev_t1, s->ev_halo, s->ev_edge})
+  for (cudaEvent_t e : {s->ev_a, s->ev_b, s->ev_t0, s->ev_t1, s->ev_halo, s->ev_edge, s->ev_s0, s->ev_s1})
     if (e) cudaEventDestroy(e);
   if (s->stream) cudaStreamDestroy(s->stream);
   if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
@@ -273,7 +276,7 @@ static int create_impl(pm_solver* s, const pm_config* cfg) {
 
   CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
-  for (cudaEvent_t* e : {&s->ev_a, &s->ev_b, &s->ev_t0, &s->ev_t1}) CK(cudaEventCreate(e));
+  for (cudaEvent_t* e : {&s->ev_a, &s->ev_b, &s->ev_t0, &s->ev_t1, &s->ev_s0, &s->ev_s1}) CK(cudaEventCreate(e));
   for (cudaEvent_t* e : {&s->ev_halo, &s->ev_edge}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 
   s->rows_alloc = nyl + 2 + 2 * k.padr;
@@ -287,9 +290,12 @@ static int create_impl(pm_solver* s, const pm_config* cfg) {
   CK(cudaMemsetAsync(s->d_state, 0, sizeof(PpeState), s->stream));
   CK(cudaMalloc(&s->d_res, size_t(c.max_iters + 2) * sizeof(unsigned long long)));
   CK(cudaMemsetAsync(s->d_res, 0, size_t(c.max_iters + 2) * sizeof(unsigned long long), s->stream));
-  const dim3 g = cell_grid(k);
-  s->n_partial = int(g.x * g.y);
-  CK(cudaMalloc(&s->d_partial, size_t(s->n_partial) * sizeof(double)));
+  {  // one partial sum per block of whichever grid writes them: the cell kernels (k_source, k_diag) or the row kernels (k_source_rows)
+    const dim3 g = cell_grid(k), gr = rows_grid(k);
+    s->n_partial = int(g.x * g.y);
+    s->cap_partial = std::max(s->n_partial, int(gr.x * gr.y));
+    CK(cudaMalloc(&s->d_partial, size_t(s->cap_partial) * sizeof(double)));
+  }
   CK(cudaMallocHost(&s->h_state, sizeof(PpeState)));
   CK(cudaMallocHost(&s->h_res, size_t(c.max_iters + 2) * sizeof(unsigned long long)));
 
@@ -404,6 +410,17 @@ static int ensure_p_split(pm_solver* s) {  // before the tiled solve reads s->tp
 }
 static void p_natural_written(pm_solver* s) { s->p_nat = true; s->p_split = false; }
 
+// The streamed host steps (pm_host_step_*) rotate u, v through three plane sets and keep downloads in flight.
+// Entry points that write u or v outside that pipeline first refuse to run between a submit and its run, then
+// wait for the pending downloads (which read the plane set the handle currently points at).
+extern "C" int pm_host_step_drain(pm_solver* s);
+static int pipe_quiesce(pm_solver* s, const char* who) {
+  if (!s->hp.ready) return PM_OK;
+  if (s->hp.submitted != s->hp.run)
+    return fail(s, PM_ERR_INVALID_ARGUMENT, "%s: %lld step(s) submitted with pm_host_step_submit and not yet run", who, s->hp.submitted - s->hp.run);
+  return pm_host_step_drain(s);
+}
+
 // ---------------------------------------------------------------------------
 // data movement
 // ---------------------------------------------------------------------------
@@ -424,6 +441,7 @@ extern "C" int pm_upload(pm_solver* s, int field, const double* host, size_t cou
   if (!dst) return fail(s, PM_ERR_INVALID_ARGUMENT, "unknown field %d", field);
   if (count != size_t(rows) * cols) return fail(s, PM_ERR_INVALID_ARGUMENT, "field %d expects %zu elements, got %zu", field, size_t(rows) * cols, count);
   CK(cudaSetDevice(s->device));
+  if (field == PM_FIELD_U || field == PM_FIELD_V) PMTRY(pipe_quiesce(s, "pm_upload"));
   int ja, jb;
   local_row_span(s, rows, true, &ja, &jb);
   const KP& k = s->kp;
@@ -472,6 +490,7 @@ static int slab_copy(pm_solver* s, int field, double* host, size_t count, bool t
   const size_t n = size_t(jb - ja + 1);
   if (count != n * cols) return fail(s, PM_ERR_INVALID_ARGUMENT, "slab of field %d expects %zu elements, got %zu", field, n * cols, count);
   CK(cudaSetDevice(s->device));
+  if (to_device && (field == PM_FIELD_U || field == PM_FIELD_V)) PMTRY(pipe_quiesce(s, "pm_upload_slab"));
   if (field == PM_FIELD_P && !to_device) PMTRY(ensure_p_natural(s));
   const KP& k = s->kp;
   if (to_device)
@@ -510,11 +529,9 @@ extern "C" int pm_download_mask(pm_solver* s, uint8_t* is_fluid, size_t count) {
 extern "C" int pm_fill_zero(pm_solver* s) {
   if (!s) return PM_ERR_INVALID_ARGUMENT;
   CK(cudaSetDevice(s->device));
+  PMTRY(pipe_quiesce(s, "pm_fill_zero"));  // u, v may currently live in one of the streaming plane sets
   CK(cudaMemsetAsync(s->base, 0, s->plane * PL_COUNT * sizeof(double), s->stream));
-  if (s->hp.ready) {  // u, v may currently live in one of the streaming plane sets
-    PMTRY(pm_host_step_drain(s));
-    CK(cudaMemsetAsync(s->hp.extra, 0, s->plane * 5 * sizeof(double), s->stream));
-  }
+  if (s->hp.ready) CK(cudaMemsetAsync(s->hp.extra, 0, s->plane * 5 * sizeof(double), s->stream));
   if (s->tp[0]) CK(cudaMemsetAsync(s->tp[0], 0, s->plane * 2 * sizeof(double), s->stream));
   s->p_cur = PL_P0;
   s->tp_cur = 0;
@@ -589,7 +606,8 @@ extern "C" int pm_apply_bc(pm_solver* s, int which) {
     k_bc_channel<<<(n + 255) / 256, 256, 0, s->stream>>>(k, U, V);
     CKL(s);
     if (k.has_mask) {
-      k_bc_solid<<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->mask, U, V);
+      const dim3 g((k.nx + PM_BX - 1) / PM_BX, (k.nyl + 2 + PM_BY - 1) / PM_BY);  // halo rows included
+      k_bc_solid<<<g, cell_block(), 0, s->stream>>>(k, s->mask, U, V);
       CKL(s);
     }
   }
@@ -626,6 +644,7 @@ extern "C" int pm_source(pm_solver* s) {
   if (!k.has_mask) {
     const dim3 g = rows_grid(k);
     n_partial = int(g.x * g.y);
+    if (n_partial > s->cap_partial) return fail(s, PM_ERR_RUNTIME, "partial-sum buffer too small: %d blocks, %d slots", n_partial, s->cap_partial);
     if (exact) k_source_rows<Exact><<<g, rows_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->pl[PL_F], s->d_state, partial);
     else k_source_rows<Fast><<<g, rows_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->pl[PL_F], s->d_state, partial);
   } else if (exact)
@@ -640,22 +659,35 @@ extern "C" int pm_source(pm_solver* s) {
     return PM_OK;
   }
   if (s->cfg.nranks > 1) {
-    if (exact) return fail(s, PM_ERR_UNSUPPORTED, "exact_arith keeps the reference's serial source sum, which does not shard; use exact_arith=0 with nranks > 1");
     std::string e;
     if (!pm_nccl_allreduce_max_u64(&s->nccl, s->stream, &s->d_state->maxf_bits, 1, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
-    k_sum_partials<<<1, 1024, 0, s->stream>>>(s->d_partial, n_partial, s->d_state);  // local sum -> ke_sum scratch
-    CKL(s);
-    if (!pm_nccl_allreduce_sum_f64(&s->nccl, s->stream, &s->d_state->ke_sum, 1, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
-    k_mean_from_sum<<<1, 1, 0, s->stream>>>(k.fluid_count_global, s->d_state);
-    CKL(s);
-    k_sub_mean<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
-    CKL(s);
+    if (exact) {
+      // the reference's serial sum, continued from slab to slab in row order (channel-01.cpp:622-625)
+      const int r = s->cfg.rank, last = s->cfg.nranks - 1;
+      if (r > 0 && !pm_nccl_recv_words(&s->nccl, s->stream, s->d_state->chain, 2, r - 1, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
+      k_mean_serial<<<1, 32, 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state, r > 0);
+      CKL(s);
+      if (r < last && !pm_nccl_send_words(&s->nccl, s->stream, s->d_state->chain, 2, r + 1, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
+      static_assert(sizeof(double) == sizeof(unsigned long long), "");
+      if (!pm_nccl_bcast_words(&s->nccl, s->stream, reinterpret_cast<unsigned long long*>(&s->d_state->mean), 1, last, &e))
+        return fail(s, PM_ERR_NCCL, "%s", e.c_str());
+      k_sub_mean<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+      CKL(s);
+    } else {
+      k_sum_partials<<<1, 1024, 0, s->stream>>>(s->d_partial, n_partial, s->d_state);  // local sum -> ke_sum scratch
+      CKL(s);
+      if (!pm_nccl_allreduce_sum_f64(&s->nccl, s->stream, &s->d_state->ke_sum, 1, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
+      k_mean_from_sum<<<1, 1, 0, s->stream>>>(k.fluid_count_global, s->d_state);
+      CKL(s);
+      k_sub_mean<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+      CKL(s);
+    }
     if (!pm_nccl_allreduce_max_u64(&s->nccl, s->stream, &s->d_state->maxf2_bits, 1, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
     s->f_max_valid = true;
     return PM_OK;
   }
   if (exact) {
-    k_mean_serial<<<1, 32, 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+    k_mean_serial<<<1, 32, 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state, 0);
     CKL(s);
     k_sub_mean<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
   } else {
@@ -726,6 +758,7 @@ static int launch_iteration_simple(pm_solver* s, int krel, int kabs) {
     if (masked) {
       k_pghost_walls<<<(std::max(k.nx, k.nyl) + 255) / 256, 256, 0, s->stream>>>(k, dst, s->d_state, s->d_res, krel);
       CKL(s);
+      PMTRY(exchange_halo1(s, dst));  // a solid cell in my edge row extrapolates from the neighbour slab's fresh fluid values
       k_pghost_solid<<<cell_grid(k), cell_block(), 0, s->stream>>>(k, dst, s->mask, s->d_state, s->d_res, krel);
       CKL(s);
     }
@@ -743,6 +776,7 @@ static int launch_iteration_simple(pm_solver* s, int krel, int kabs) {
     if (masked) {
       k_pghost_walls<<<(std::max(k.nx, k.nyl) + 255) / 256, 256, 0, s->stream>>>(k, p, s->d_state, s->d_res, krel);
       CKL(s);
+      PMTRY(exchange_halo1(s, p));  // a solid cell in my edge row extrapolates from the neighbour slab's fresh fluid values
       k_pghost_solid<<<cell_grid(k), cell_block(), 0, s->stream>>>(k, p, s->mask, s->d_state, s->d_res, krel);
       CKL(s);
     }
@@ -1119,10 +1153,11 @@ extern "C" int pm_ppe_solve(pm_solver* s, pm_ppe_result* out) {
   return PM_OK;
 }
 
-extern "C" int pm_step(pm_solver* s, int nsteps, pm_ppe_result* last) {
-  if (!s || nsteps < 0) return PM_ERR_INVALID_ARGUMENT;
+static int step_impl(pm_solver* s, int nsteps, pm_ppe_result* last) {
   pm_ppe_result r{};
   for (int n = 0; n < nsteps; ++n) {
+    const double ppe_before = s->timing.ppe_ms;
+    CK(cudaEventRecord(s->ev_s0, s->stream));
     if (s->kp.case_id == PM_CASE_CAVITY) {  // cavity-01.cpp:387-390
       PMTRY(pm_apply_bc(s, 0));
       if (s->cfg.nranks == 1 || s->kp.nyl >= 2) {
@@ -1141,9 +1176,19 @@ extern "C" int pm_step(pm_solver* s, int nsteps, pm_ppe_result* last) {
       PMTRY(pm_correct(s));
       PMTRY(pm_apply_bc(s, 0));
     }
+    CK(cudaEventRecord(s->ev_s1, s->stream));
+    s->step_timed = true;
+    s->last_step_ppe_ms = s->timing.ppe_ms - ppe_before;
   }
   if (last) *last = r;
   return PM_OK;
+}
+
+extern "C" int pm_step(pm_solver* s, int nsteps, pm_ppe_result* last) {
+  if (!s || nsteps < 0) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  PMTRY(pipe_quiesce(s, "pm_step"));
+  return step_impl(s, nsteps, last);
 }
 
 // ---------------------------------------------------------------------------
@@ -1218,7 +1263,7 @@ extern "C" int pm_host_step_run(pm_solver* s, pm_ppe_result* r) {
   CK(cudaStreamWaitEvent(s->stream, h.ev_up[set], 0));
   s->pl[PL_U] = h.u[set];
   s->pl[PL_V] = h.v[set];
-  PMTRY(pm_step(s, 1, r));
+  PMTRY(step_impl(s, 1, r));
   // results: p leaves through its own plane (the next solve overwrites both pressure buffers); u, v stay where
   // they are -- the next two steps use the other plane sets
   if (h.pdown_pending) CK(cudaStreamWaitEvent(s->stream, h.ev_pdown, 0));
@@ -1281,6 +1326,13 @@ extern "C" int pm_diagnostics(pm_solver* s, double* max_div, double* avg_ke) {
 
 extern "C" int pm_get_timing(pm_solver* s, pm_timing* t) {
   if (!s || !t) return PM_ERR_INVALID_ARGUMENT;
+  if (s->step_timed) {  // the non-pressure phases of the most recent pm_step: its device time minus its pressure solve
+    CK(cudaSetDevice(s->device));
+    CK(cudaEventSynchronize(s->ev_s1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, s->ev_s0, s->ev_s1));
+    s->timing.other_ms = std::max(0.0, double(ms) - s->last_step_ppe_ms);
+  }
   *t = s->timing;
   return PM_OK;
 }

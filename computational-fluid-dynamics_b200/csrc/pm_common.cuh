@@ -189,6 +189,7 @@ struct PpeState {
   int pad_;
   double ke_sum;   // diagnostics scratch
   unsigned long long div_bits;
+  unsigned long long chain[2];  // exact source mean over slabs: running serial sum (bits) and cell count handed from rank to rank
 };
 
 // The reference's loop test `while (res > tol && it < max)` evaluated for entering iteration k

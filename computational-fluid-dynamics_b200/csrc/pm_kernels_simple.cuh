@@ -69,17 +69,21 @@ __global__ void k_bc_channel(const __grid_constant__ KP k, double* __restrict__ 
 
 // backwards_step-01.cpp:654-682: zero the faces between a solid cell and a fluid neighbour.
 // Runs after k_bc_channel (the wall ghosts read the pre-zero values, as in the reference).
+// Slabs: local rows 0 and nyl+1 are the neighbour slabs' edge rows (their mask rows were uploaded with the
+// halo): a solid cell there owns the v face below / above it that lies in THIS slab, so the halo rows are
+// visited too; faces that would need mask rows beyond the halo are the neighbour's own business.
 __global__ void k_bc_solid(const __grid_constant__ KP k, const uint8_t* __restrict__ M, double* __restrict__ U,
                            double* __restrict__ V) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  if (i > k.nx || jl > k.nyl) return;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y;  // 0 .. nyl+1
+  if (i > k.nx || jl > k.nyl + 1) return;
   const int j = k.j0 + jl;
+  if (j < 1 || j > k.ny) return;  // the reference visits interior cells only
   if (M[pm_idx(k, jl, i)]) return;
   if (i < k.nx && M[pm_idx(k, jl, i + 1)]) U[pm_idx(k, jl, i)] = 0.0;
   if (i > 1 && M[pm_idx(k, jl, i - 1)]) U[pm_idx(k, jl, i - 1)] = 0.0;
-  if (j < k.ny && M[pm_idx(k, jl + 1, i)]) V[pm_idx(k, jl, i)] = 0.0;
-  if (j > 1 && M[pm_idx(k, jl - 1, i)]) V[pm_idx(k, jl - 1, i)] = 0.0;
+  if (jl <= k.nyl && j < k.ny && M[pm_idx(k, jl + 1, i)]) V[pm_idx(k, jl, i)] = 0.0;
+  if (jl >= 1 && j > 1 && M[pm_idx(k, jl - 1, i)]) V[pm_idx(k, jl - 1, i)] = 0.0;
 }
 
 // ---------------------------------------------------------------------------
@@ -345,12 +349,14 @@ __global__ void k_mean_from_partials(const double* __restrict__ partial, int n, 
 }
 __global__ void k_mean_from_sum(int count, PpeState* __restrict__ st) { st->mean = count > 0 ? st->ke_sum / double(count) : 0.0; }
 // k5 (exact policy): the reference's serial row-major sum (channel-01.cpp:622-625), one warp,
-// every lane adding the same 32 shuffled values in index order.
+// every lane adding the same 32 shuffled values in index order.  Slabs: the running sum and count enter
+// through st->chain (zero on the first rank) and leave through it, so the chain of ranks performs the
+// reference's additions in the reference's order; the last rank's mean is the global one.
 __global__ void k_mean_serial(const __grid_constant__ KP k, const double* __restrict__ f, const uint8_t* __restrict__ M,
-                              PpeState* __restrict__ st) {
+                              PpeState* __restrict__ st, int chained) {
   const int lane = threadIdx.x;
-  double s = 0.0;
-  int cnt = 0;
+  double s = chained ? __longlong_as_double((long long)st->chain[0]) : 0.0;
+  long long cnt = chained ? (long long)st->chain[1] : 0;
   for (int jl = 1; jl <= k.nyl; ++jl)
     for (int ib = 1; ib <= k.nx; ib += 32) {
       const int i = ib + lane;
@@ -368,7 +374,11 @@ __global__ void k_mean_serial(const __grid_constant__ KP k, const double* __rest
         if (uq) { s = __dadd_rn(s, xq); ++cnt; }
       }
     }
-  if (lane == 0) st->mean = cnt > 0 ? __ddiv_rn(s, double(cnt)) : 0.0;
+  if (lane == 0) {
+    st->mean = cnt > 0 ? __ddiv_rn(s, double(cnt)) : 0.0;
+    st->chain[0] = (unsigned long long)__double_as_longlong(s);
+    st->chain[1] = (unsigned long long)cnt;
+  }
 }
 // k5/k6: f -= mean on (fluid) cells when max|f| > 0, and max|f| of the result
 // (channel-01.cpp:621-628, :643-646).

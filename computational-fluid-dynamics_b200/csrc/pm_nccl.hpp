@@ -21,6 +21,7 @@ struct PmNccl {
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -43,6 +44,7 @@ static inline bool pm_nccl_load(PmNccl* n, std::string* err) {
   PM_SYM(Send, "ncclSend")
   PM_SYM(Recv, "ncclRecv")
   PM_SYM(AllReduce, "ncclAllReduce")
+  PM_SYM(Broadcast, "ncclBroadcast")
   PM_SYM(GroupStart, "ncclGroupStart")
   PM_SYM(GroupEnd, "ncclGroupEnd")
   PM_SYM(GetErrorString, "ncclGetErrorString")
@@ -96,5 +98,18 @@ static inline bool pm_nccl_allreduce_max_u64(PmNccl* n, cudaStream_t st, unsigne
 }
 static inline bool pm_nccl_allreduce_sum_f64(PmNccl* n, cudaStream_t st, double* buf, size_t cnt, std::string* err) {
   PM_NCCL_CK(n->AllReduce(buf, buf, cnt, ncclDouble, ncclSum, n->comm, st));
+  return true;
+}
+// A few 64-bit words along the slab chain (the exact source mean): from rank-1, then on to rank+1.
+static inline bool pm_nccl_recv_words(PmNccl* n, cudaStream_t st, unsigned long long* buf, size_t cnt, int peer, std::string* err) {
+  PM_NCCL_CK(n->Recv(buf, cnt, ncclUint64, peer, n->comm, st));
+  return true;
+}
+static inline bool pm_nccl_send_words(PmNccl* n, cudaStream_t st, const unsigned long long* buf, size_t cnt, int peer, std::string* err) {
+  PM_NCCL_CK(n->Send(buf, cnt, ncclUint64, peer, n->comm, st));
+  return true;
+}
+static inline bool pm_nccl_bcast_words(PmNccl* n, cudaStream_t st, unsigned long long* buf, size_t cnt, int root, std::string* err) {
+  PM_NCCL_CK(n->Broadcast(buf, buf, cnt, ncclUint64, root, n->comm, st));
   return true;
 }

@@ -178,7 +178,9 @@ int pm_step(pm_solver* s, int nsteps, pm_ppe_result* last);
  *   pm_host_step_drain   blocks until every enqueued download has landed in host memory.
  * Copies run on their own streams through three rotating (u, v) plane sets, so the upload of step n+1 and the
  * download of step n-1 overlap the kernels of step n.  At most two steps may be submitted and not yet run.
- * The host buffers of a step must stay valid and untouched until pm_host_step_drain returns. */
+ * The host buffers of a step must stay valid and untouched until pm_host_step_drain returns.
+ * While a step is submitted and not yet run, pm_step, pm_fill_zero / pm_fill_random* and uploads of u or v return
+ * PM_ERR_INVALID_ARGUMENT; once every submitted step has run they wait for the pending downloads first. */
 int pm_host_step_submit(pm_solver* s, const double* u_in, size_t u_count, const double* v_in, size_t v_count,
                         double* u_out, double* v_out, double* p_out, size_t p_count);
 int pm_host_step_run(pm_solver* s, pm_ppe_result* r);
@@ -193,8 +195,8 @@ int pm_sync(pm_solver* s);
 
 /* ---- measurement helpers ------------------------------------------------ */
 typedef struct pm_timing {
-  double ppe_ms;        /* device time in PPE kernels during the last pm_step/pm_ppe_solve */
-  double other_ms;      /* device time of the other phases of the last pm_step */
+  double ppe_ms;        /* device time spent in pm_ppe_solve since creation (cumulative; take differences) */
+  double other_ms;      /* device time of the non-pressure phases of the most recent projection step (pm_get_timing waits for it) */
   int64_t kernel_launches; /* kernels launched by this handle since creation */
   int64_t ppe_passes;   /* PPE kernel passes since creation */
 } pm_timing;

@@ -27,11 +27,15 @@ CASES = {
     "cavity_k50_32": ("cavity_k50_32", 5),       # 32x32, 50-iteration cap
     "channel_k50": ("channel_k50", 5),           # 93x31, 50-iteration cap
     "step_k50": ("step_k50", 5),                 # 256x32, 50-iteration cap
+    "step_default_20": ("step_default", 20),     # longer horizon: 20 steps, every one of them ends at the 10 000 cap
 }
 
 
 def main():
+    only = sys.argv[1:]
     for name, (build, steps) in CASES.items():
+        if only and name not in only:
+            continue
         R = orc.Reference(build)
         prm = R.params()
         iters, res = [], []

@@ -54,6 +54,14 @@ def main():
         (pm.CASE_CAVITY, 1100, 600, pm.PPE_SOR_RB, 1, pm.PATH_TILED, 4, 22, 1),   # deepest halo (8 rows = all pad rows)
         (pm.CASE_CHANNEL, 600, 333, pm.PPE_SOR_RB, 0, pm.PATH_AUTO, 0, 21, 2),    # production path as the drivers run it: T = 4, split-row buffers, row kernels
         (pm.CASE_CAVITY, 64, 64, pm.PPE_SOR_RB, 1, pm.PATH_SIMPLE, 0, 10000, 2),  # run to tolerance: same stopping iterate
+        # exact arithmetic for channel/step: the reference's serial source mean is continued from slab to slab
+        (pm.CASE_CHANNEL, 300, 50, pm.PPE_SOR_RB, 1, pm.PATH_SIMPLE, 0, 30, 2),
+        (pm.CASE_CHANNEL, 300, 50, pm.PPE_SOR_RB, 1, pm.PATH_TILED, 4, 30, 2),
+        # obstacle mask; with 2 ranks and even ny the slab cut falls exactly on inlet_j_max (the top wall of the inlet channel)
+        (pm.CASE_STEP, 256, 16, pm.PPE_SOR_RB, 1, pm.PATH_SIMPLE, 0, 30, 3),
+        (pm.CASE_STEP, 256, 16, pm.PPE_JACOBI, 1, pm.PATH_SIMPLE, 0, 30, 3),
+        (pm.CASE_STEP, 320, 45, pm.PPE_SOR_RB, 0, pm.PATH_AUTO, 0, 25, 2),
+        (pm.CASE_STEP, 256, 16, pm.PPE_SOR_RB, 1, pm.PATH_SIMPLE, 0, 10000, 2),
     ]
     failures = 0
     for (case, nx, nyr, method, exact, path, T, K, steps) in cases:

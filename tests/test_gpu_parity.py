@@ -160,18 +160,74 @@ def test_whole_steps_and_stopping_rule_bit_exact(pm, orc, case_id, nx, ny, steps
     assert_fields_equal(S, O, range(6), "whole steps")
 
 
-@pytest.mark.parametrize("name,steps", [("cavity_default", 4), ("channel_default", 3)])
-def test_red_black_to_tolerance_matches_reference_golden(pm, name, steps):
-    """Production ordering vs the reference's own fields (golden, lexicographic SOR): 1e-6 relative L2."""
+def golden_cfg(pm, g, method, exact, max_iters=None):
+    """pm_config carrying exactly the parameters the reference build of a golden fixture ran with."""
+    cfg = pm.config_init(int(g["case_id"]), int(g["prm_nx"]), int(g["prm_ny"]))
+    cfg.dt, cfg.omega, cfg.nu = float(g["prm_dt"]), float(g["prm_omega"]), float(g["prm_nu"])
+    cfg.dx, cfg.dy = float(g["prm_dx"]), float(g["prm_dy"])
+    cfg.max_iters = int(g["prm_max_iters"]) if max_iters is None else max_iters
+    cfg.ppe_method, cfg.exact_arith = method, exact
+    return cfg
+
+
+# Production red-black (FMA arithmetic) against the reference's OWN fields (golden, lexicographic SOR, recorded from
+# the unmodified reference) on its default programs and on BASELINE configs[0..2].  north_star's bar is 1e-6 relative
+# L2.  It holds wherever the reference converges within its 10 000-iteration cap.  Where the reference itself stops
+# at the cap unconverged (configs[1]: residual 47.8 against a tolerance of 0.0168 after step 1; configs[2]: 2.1
+# against 6e-4) neither ordering has solved the Poisson problem and the two capped iterates differ by what is left
+# of the error; the bounds below are the measured gaps (CPU oracle red-black vs golden: see the comments) times ~4.
+# v is measured against the velocity scale |(u, v)|: in the channel's first step v is ~1e-10 of u.
+#   name, steps, bound u, bound v / |(u,v)|, bound p
+REFERENCE_GOLDEN_RUNS = [
+    ("cavity_default", 4, 1e-6, 1e-6, 1e-6),      # measured 1.4e-10, 5.2e-8, 4.6e-8
+    ("channel_default", 3, 1e-6, 1e-6, 1e-6),     # measured 1.5e-8, 4.8e-7 (v itself), 5.4e-7
+    ("cavity_cfg0", 2, 1e-6, 1e-6, 1e-6),         # BASELINE configs[0]: measured 9.9e-10, 2.1e-7, 5.9e-8
+    ("channel_cfg1", 1, 1e-3, 1e-3, 1e-3),        # BASELINE configs[1], reference capped unconverged: measured 2.1e-4, 2.3e-4, 2.5e-4
+    ("step_default", 2, 1e-3, 1e-3, 5e-2),        # BASELINE configs[2], reference capped unconverged: measured 2.3e-4, 2.5e-4, 1.3e-2
+    ("step_default_20", 20, 1e-5, 1e-5, 2e-5),    # same run 18 steps on (17 of 20 capped): the warm starts pull both together: 1.7e-6, 1.7e-6, 3.4e-6
+]
+
+
+@pytest.mark.parametrize("name,steps,bu,bv,bp", REFERENCE_GOLDEN_RUNS)
+def test_red_black_to_tolerance_matches_reference_golden(pm, name, steps, bu, bv, bp):
     g = load_golden(name)
-    case_id = int(g["case_id"])
-    cfg = make_cfg(pm, case_id, int(g["prm_nx"]), int(g["prm_ny"]), RB, 0, 10000)
-    assert cfg.dt == float(g["prm_dt"]) and cfg.omega == float(g["prm_omega"])
+    assert int(g["steps"]) == steps
+    cfg = golden_cfg(pm, g, RB, 0)
+    chk = pm.config_init(int(g["case_id"]), int(g["prm_nx"]), int(g["prm_ny"]))
+    if name in ("cavity_default", "channel_default", "step_default", "step_default_20"):
+        assert chk.dt == cfg.dt and chk.omega == cfg.omega  # pm_config_init derives the reference's own constants
     S = pm.Solver(cfg)
     S.apply_bc(0)
     S.step(steps)
-    for fid in (0, 1, 2):
-        assert rel_l2(S.download(fid), g[f"f{fid}"]) < 1e-6, f"field {fid}"
+    u, v, p = (S.download(f) for f in (0, 1, 2))
+    gu, gv, gp = (g[f"f{f}"] for f in (0, 1, 2))
+    assert np.isfinite(u).all() and np.isfinite(v).all() and np.isfinite(p).all()
+    vel = np.sqrt(np.linalg.norm(gu) ** 2 + np.linalg.norm(gv) ** 2)
+    eu, ev, ep = rel_l2(u, gu), np.linalg.norm(v - gv) / vel, rel_l2(p, gp)
+    assert eu < bu and ev < bv and ep < bp, (eu, ev, ep)
+
+
+@pytest.mark.parametrize("name,steps", [("channel_cfg1", 1), ("step_default", 2)])
+def test_red_black_converged_matches_reference_algorithm_on_capped_configs(pm, orc, name, steps):
+    """BASELINE configs[1] and [2] with the cap lifted and the tolerance tightened on BOTH sides (tolerance_factor
+    1e-10, the reference's 1e-7 leaves a 1e-5 relative gap in p between any two orderings that merely satisfy it):
+    production red-black on the GPU against the reference's algorithm (oracle, lexicographic SOR, itself pinned bit for
+    bit to the reference at the cap) -> 1e-6 relative L2 (measured on the CPU oracle: 6e-11 / 5e-11 abs / 4e-11 and
+    9e-11 / 2e-10 / 4e-9).  ~40 000 sweeps per step."""
+    g = load_golden(name)
+    cfg = golden_cfg(pm, g, RB, 0, 2_000_000)
+    cfg.tol_factor = 1e-10
+    ocfg = cfg.copy()
+    ocfg.ppe_method = LEX
+    S, O = pm.Solver(cfg), orc.Oracle(ocfg)
+    S.apply_bc(0); O.apply_bc(0)
+    for n in range(steps):
+        rs, ro = S.step(1), O.step(1)
+        assert not rs.hit_cap and not ro.hit_cap and rs.residual <= rs.tolerance
+    u, v, p = (S.download(f) for f in (0, 1, 2))
+    ou, ov, op = (O.field(f) for f in (0, 1, 2))
+    vel = np.sqrt(np.linalg.norm(ou) ** 2 + np.linalg.norm(ov) ** 2)
+    assert rel_l2(u, ou) < 1e-6 and np.linalg.norm(v - ov) / vel < 1e-6 and rel_l2(p, op) < 1e-6
 
 
 @pytest.mark.parametrize("name", ["cavity_k50_32", "channel_k50", "step_k50"])

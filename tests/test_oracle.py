@@ -6,7 +6,7 @@ import pytest
 from conftest import bits_equal, load_golden, rel_l2
 
 GOLDEN_CASES = ["cavity_default", "channel_default", "step_default", "cavity_k50_32", "channel_k50", "step_k50"]
-SLOW_GOLDEN = ["cavity_cfg0", "channel_cfg1"]
+SLOW_GOLDEN = ["cavity_cfg0", "channel_cfg1", "step_default_20"]
 
 
 def oracle_from_golden(orc, g):

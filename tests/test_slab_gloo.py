@@ -88,6 +88,11 @@ def _worker(rank, world, port, case_id, nx, ny, K, T, mode, out_dir):
             O.sweep_rows(1, ja, jb)
             if case_id != 0:
                 _ghosts(O, p, nx, ny, ja, jb, rank, world)
+            if case_id == 2:
+                # the solid cells of my edge rows extrapolate from the neighbour slab's fresh fluid values
+                # (pm_capi.cu launch_iteration_simple: exchange, k_pghost_solid, exchange)
+                _exchange(p, ja, jb, 1, rank, world)
+                _solid_ghosts(O.mask(), p, nx, ny, ja, jb)
             _exchange(p, ja, jb, 1, rank, world)
             res_hist.append(_allreduce_max(O.residual_rows(ja, jb)))
     else:
@@ -123,6 +128,56 @@ def _ghosts(O, p, nx, ny, a, b, rank, world):
         p[0, 1:nx + 1] = p[1, 1:nx + 1]
     if rank + 1 == world:
         p[ny + 1, 1:nx + 1] = p[ny, 1:nx + 1]
+
+
+def _solid_ghosts(mask, p, nx, ny, a, b):
+    """Solid-cell extrapolation of applyPressureGhosts (backwards_step-01.cpp:709-739) on rows a..b: only solid
+    cells are written and only fluid cells are read, so the visiting order does not matter."""
+    for j in range(a, b + 1):
+        for i in range(1, nx + 1):
+            if mask[j, i]:
+                continue
+            s, n = 0.0, 0
+            if i > 1 and mask[j, i - 1]:
+                s += p[j, i - 1]; n += 1
+            if i < nx and mask[j, i + 1]:
+                s += p[j, i + 1]; n += 1
+            if j > 1 and mask[j - 1, i]:
+                s += p[j - 1, i]; n += 1
+            if j < ny and mask[j + 1, i]:
+                s += p[j + 1, i]; n += 1
+            if n > 0:
+                p[j, i] = s / n
+
+
+def test_step_case_slabs_equal_single_domain(tmp_path):
+    """The obstacle mask with the slab cut exactly on inlet_j_max (the top wall of the inlet channel; 2 slabs, even ny)
+    and off it (3 slabs): general-path schedule with the extra exchange around the solid-cell extrapolation."""
+    orc, _ = _setup()
+    for world in (2, 3):
+        case_id, nx, ny, K = 2, 32, 24, 6
+        out = tmp_path / f"w{world}"
+        out.mkdir()
+        port = 29500 + (os.getpid() * 11 + world * 17) % 2000
+        mp.spawn(_worker, args=(world, port, case_id, nx, ny, K, 1, "general", str(out)), nprocs=world, join=True)
+        cfg = orc.config_init(case_id, nx, ny)
+        assert cfg.inlet_j_max == ny // 2
+        cfg.ppe_method, cfg.max_iters = 1, K
+        O = orc.Oracle(cfg)
+        O.fill_random(99)
+        p = O.field(2)
+        res = []
+        for k in range(K):
+            O.sweep_rows(0, 1, ny)
+            O.sweep_rows(1, 1, ny)
+            O.pressure_ghosts()
+            res.append(O.residual_rows(1, ny))
+        got = np.concatenate([np.load(out / f"p_{r}.npy") for r in range(world)], axis=0)
+        a, b = got.copy(), p.copy()
+        for arr in (a, b):
+            arr[0, 0] = arr[0, -1] = arr[-1, 0] = arr[-1, -1] = 0.0
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+        assert np.array_equal(np.load(out / "res.npy"), np.array(res))
 
 
 @pytest.mark.parametrize("world", [2, 3])
