@@ -10,8 +10,17 @@ lowered); the reference tolerance stays in place and is never met a
 
 One JSON line on stdout (rank 0).  `--impl reference` times the reference's own CPU code
 (oracle/_ref, built from the unmodified sources) on a bounded sample of the same workload.
+
+Beside the contract keys the line carries
+  parity_check   the benchmarked (tiled, production-arithmetic) run compared with a general-path run of the same
+                 steps on the same inputs (rel. L-inf of u, v, p; all finite), and for N > 1 a small exact-arithmetic
+                 slab run compared bit for bit with the same problem on one GPU;
+  secondary      K = 1 (the non-pressure passes), and the channel / backwards-step forms on a large grid;
+  small_configs  BASELINE configs[0..2] at their real tolerances: ms/step on the GPU and of the reference on one core;
+  weak_base      N > 1 only: the same 16384^2 slab timed on ONE GPU in this very run (the base of weak-scaling efficiency).
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -38,6 +47,29 @@ def measured_peaks():
     if os.path.exists(p):
         return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def kernel_source_id():
+    """Identity of the build the ncu traffic figure belongs to: md5 over the sources of the tiled pressure kernel."""
+    h = hashlib.md5()
+    for f in ("pm_kernels_tiled.cuh", "pm_tile_cfg.cuh", "pm_common.cuh"):
+        h.update(open(os.path.join(ROOT, "computational-fluid-dynamics_b200", "csrc", f), "rb").read())
+    return h.hexdigest()
+
+
+def measured_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the ncu capture of THIS build (profiles/r02_traffic.json,
+    written by tools/ncu_traffic.py from `ncu --set full`); None when the kernel sources changed since that capture."""
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(tpath):
+        return None, "no ncu capture on record"
+    t = json.load(open(tpath))
+    if t.get("kernel_source_md5") != kernel_source_id():
+        return None, "kernel sources changed since the ncu capture on record"
+    e = t.get("entries", {}).get(key)
+    if not e:
+        return None, f"no ncu capture for {key}"
+    return e["dram_bytes_per_launch"], e.get("source")
 
 
 class ClockSampler(threading.Thread):
@@ -127,7 +159,173 @@ def run_reference(args):
     emit(line)
 
 
+def nccl_id_bytes(pm, dist, rank):
+    import ctypes as C
+    import torch
+    idt = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = (C.c_uint8 * 128)()
+        assert pm.lib().pm_nccl_unique_id(buf) == 0
+        idt = torch.tensor(list(buf), dtype=torch.uint8)
+    idt = idt.cuda()
+    dist.broadcast(idt, 0)
+    return idt.cpu().tolist()
+
+
+def bench_cfg(pm, case, nx, ny, k_iters, args, local, path=None):
+    """The synthetic benchmark configuration of one case on an nx x ny grid with a K-iteration cap."""
+    if case == "cavity":
+        cfg = pm.config_init(pm.CASE_CAVITY, nx, ny, 1000.0, 0.0)
+        # The reference enters its loop only if 1.0 > tolerance_factor * max|f| (cavity-01.cpp:618,632,635).  At
+        # h = 1/8192 the lid corners alone give max|f| = 2*nu*U/h^3 = 1.1e9, so with the compiled-in 1e-9 the
+        # solver would not sweep at all; 1e-12 keeps the rule in force and lets the K-iteration cap end the loop.
+        cfg.tol_factor = 1e-12
+    else:
+        cfg = pm.config_init(pm.CASE_CHANNEL if case == "channel" else pm.CASE_STEP, nx, ny, 1000.0 if case == "channel" else 100.0, 0.0)
+    cfg.max_iters = k_iters
+    cfg.ppe_method = {"rb": pm.PPE_SOR_RB, "jacobi": pm.PPE_JACOBI}[args.ppe]
+    if args.ppe == "jacobi":
+        cfg.omega = 1.0
+    cfg.exact_arith = args.exact
+    cfg.kernel_path = args.path if path is None else path
+    cfg.sweeps_per_pass = args.sweeps
+    cfg.device = local
+    return cfg
+
+
+def init_state(S, case):
+    # u, v ~ 2^-10 * U(-1,1) by global flat index (SURVEY 8d); p cold-starts in the cavity.  The amplitude keeps
+    # max|f| < 1e9: with U(-1,1) at h = 1/8192 the reference's own loop test (res = 1.0 > 1e-9*max|f|,
+    # cavity-01.cpp:618,632,635) is false before the first sweep and the solver would do no work at all.
+    S.fill_random(42, 2.0 ** -10)
+    if case != "cavity":
+        S.apply_bc(0)  # the channel / step constructors apply the BCs once before the loop (channel-01.cpp:352)
+
+
+def device_timed(S, steps, warmup):
+    """ms per step with the handle's own CUDA events, after `warmup` untimed steps."""
+    for _ in range(warmup):
+        S.step(1)
+    S.sync()
+    S.timer_start()
+    for _ in range(steps):
+        r = S.step(1)
+    return S.timer_stop() / steps, r
+
+
+def secondary_lines(pm, args, local):
+    """Single-GPU side measurements: K = 1 (what is left when the pressure loop is one sweep) and the other two
+    forms of the path (channel: dx != dy, in-tile wall ghosts, source mean; step: obstacle mask) on 8192 x 2048."""
+    out = {}
+    n = args.n or 8192
+    cfg = bench_cfg(pm, "cavity", n, n, 1, args, local)
+    S = pm.Solver(cfg)
+    init_state(S, "cavity")
+    ms, r = device_timed(S, 10, 3)
+    S.close()
+    out["k1_cavity"] = {"workload": f"cavity {n}x{n}, K=1", "ms_per_step": ms, "value": n * n / ms / 1e3, "unit": UNIT,
+                        "algorithmic_GBps": bytes_per_cell_step(1) * n * n / ms / 1e6}
+    for case in ("channel", "step"):
+        nx, ny = (n, n // 4)
+        cfg = bench_cfg(pm, case, nx, ny, K_ITERS, args, local)
+        S = pm.Solver(cfg)
+        init_state(S, case)
+        t0 = S.timing()
+        ms, r = device_timed(S, 6, 2)
+        t1 = S.timing()
+        S.close()
+        out[f"{case}_{nx}x{ny}"] = {"workload": f"{case} {nx}x{ny}, K={K_ITERS} red-black iterations/step, residual every iteration",
+                                    "ms_per_step": ms, "value": nx * ny / ms / 1e3, "unit": UNIT, "iterations": r.iterations,
+                                    "algorithmic_GBps": bytes_per_cell_step(K_ITERS) * nx * ny / ms / 1e6,
+                                    "launches_per_step": (t1.kernel_launches - t0.kernel_launches) / 8}
+    return out
+
+
+SMALL_CONFIGS = [
+    ("configs[0] cavity Re=100 128x128 dt=1e-3", "cavity", (128, 128, 100.0, 1e-3), "cavity_cfg0"),
+    ("configs[1] channel Re=1000 256x64 dt=5e-4", "channel", (256, 64, 1000.0, 5e-4), "channel_cfg1"),
+    ("configs[2] backwards step Re=100 256x32 (mask)", "step", (0, 0, 0.0, 0.0), "step_default"),
+]
+
+
+def small_configs(pm, local, with_cpu):
+    """BASELINE configs[0..2] exactly as the reference runs them (real tolerances, 10 000 cap): wall ms per step of the
+    production path (red-black, persistent cluster solve) and of the unmodified reference on one host core."""
+    rows = []
+    for name, case, a, refname in SMALL_CONFIGS:
+        cid = {"cavity": pm.CASE_CAVITY, "channel": pm.CASE_CHANNEL, "step": pm.CASE_STEP}[case]
+        cfg = pm.config_init(cid, *a)
+        cfg.ppe_method, cfg.device = pm.PPE_SOR_RB, local
+        S = pm.Solver(cfg)
+        S.apply_bc(0)
+        S.step(2)
+        S.sync()
+        t0 = time.perf_counter()
+        iters, steps = 0, 10
+        for _ in range(steps):
+            iters += S.step(1).iterations
+        S.sync()
+        dt = time.perf_counter() - t0
+        S.close()
+        row = {"config": name, "gpu_ms_per_step": 1e3 * dt / steps, "gpu_iterations_per_step": iters / steps,
+               "gpu_us_per_iteration": 1e6 * dt / max(iters, 1), "ordering": "red-black (production); the reference's is lexicographic"}
+        if with_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import orc
+            if orc.ref_available(refname):
+                R = orc.Reference(refname)
+                R.step(2)
+                it, n = 0, 3
+                t0 = time.perf_counter()
+                for _ in range(n):
+                    it += R.step(1)[0]
+                dt = time.perf_counter() - t0
+                row.update({"reference_cpu_ms_per_step": 1e3 * dt / n, "reference_iterations_per_step": it / n, "reference_kind": "oracle/_ref (unmodified reference), 1 core"})
+        rows.append(row)
+    return rows
+
+
+def slabs_bit_equal(pm, dist, rank, world, local):
+    """One small exact-arithmetic problem (tiled path, T = 4, several tile rows per slab) solved on `world` slabs and,
+    on rank 0, on one GPU: the union of the slabs must equal the single-GPU u, v, p bit for bit."""
+    import numpy as np
+    import torch
+    nx, nyr, K, steps = 1100, 600, 22, 1
+    ny = nyr * world
+    cfg = pm.config_init(pm.CASE_CAVITY, nx, ny)
+    cfg.ppe_method, cfg.exact_arith, cfg.kernel_path, cfg.sweeps_per_pass, cfg.max_iters, cfg.device = pm.PPE_SOR_RB, 1, pm.PATH_TILED, 4, K, local
+    single = None
+    if rank == 0:
+        S1 = pm.Solver(cfg)
+        S1.fill_random(5, 2.0 ** -4)
+        r1 = S1.step(steps)
+        single = [S1.download(f) for f in (pm.F_U, pm.F_V, pm.F_P)]
+        S1.close()
+    mcfg = cfg.copy()
+    mcfg.rank, mcfg.nranks = rank, world
+    for q, b in enumerate(nccl_id_bytes(pm, dist, rank)):
+        mcfg.nccl_id[q] = b
+    S = pm.Solver(mcfg)
+    S.fill_random(5, 2.0 ** -4)
+    r = S.step(steps)
+    ok = True
+    for q, f in enumerate((pm.F_U, pm.F_V, pm.F_P)):
+        a = np.zeros(pm.field_shape(f, nx, ny))
+        S.download(f, a)
+        t = torch.from_numpy(a.view(np.int64).copy()).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)  # rows are disjoint over ranks and zero elsewhere
+        if rank == 0:
+            ok = ok and np.array_equal(t.cpu().numpy(), single[q].view(np.int64))
+    S.close()
+    if rank == 0:
+        ok = ok and (r.iterations, r.residual) == (r1.iterations, r1.residual)
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(t, 0)
+    return bool(t.item()), f"cavity {nx}x{ny} on {world} slabs vs 1 GPU, exact arithmetic, tiled T=4, K={K}: u, v, p, iterations, residual"
+
+
 def run_ours(args):
+    import numpy as np
     import torch
     import pm_ctypes as pm
     rank = int(os.environ.get("RANK", "0"))
@@ -142,49 +340,44 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    if world == 1:
-        nx = ny_local = args.n or 8192
-        workload = f"lid-driven cavity Re=1000 {nx}x{nx} on 1 B200 (BASELINE configs[3])"
+    case = args.case
+    if case == "cavity":
+        if world == 1:
+            nx = ny_local = args.n or 8192
+            workload = f"lid-driven cavity Re=1000 {nx}x{nx} on 1 B200 (BASELINE configs[3])"
+        else:
+            nx = ny_local = args.n or 16384
+            workload = f"lid-driven cavity Re=1000 {nx}x{ny_local * world}, {nx}x{ny_local} per GPU, {world} j-slabs (BASELINE configs[4])"
     else:
-        nx = ny_local = args.n or 16384
-        workload = f"lid-driven cavity Re=1000 {nx}x{ny_local * world}, {nx}x{ny_local} per GPU, {world} j-slabs (BASELINE configs[4])"
+        nx = args.n or 8192
+        ny_local = nx // 4
+        workload = f"{case} flow {nx}x{ny_local * world} ({nx}x{ny_local} per GPU), large-grid form of BASELINE configs[{1 if case == 'channel' else 2}]"
     ny = ny_local * world
-    cfg = pm.config_init(pm.CASE_CAVITY, nx, ny, 1000.0, 0.0)
-    cfg.max_iters = K_ITERS
-    # The reference enters its loop only if 1.0 > tolerance_factor * max|f| (cavity-01.cpp:618,632,635).  At
-    # h = 1/8192 the lid corners alone give max|f| = 2*nu*U/h^3 = 1.1e9, so with the compiled-in 1e-9 the
-    # solver would not sweep at all; 1e-12 keeps the rule in force and lets the K-iteration cap end the loop.
-    cfg.tol_factor = 1e-12
-    cfg.ppe_method = {"rb": pm.PPE_SOR_RB, "jacobi": pm.PPE_JACOBI}[args.ppe]
-    if args.ppe == "jacobi":
-        cfg.omega = 1.0
-    cfg.exact_arith = args.exact
-    cfg.kernel_path = args.path
-    cfg.sweeps_per_pass = args.sweeps
-    cfg.device = local
-    cfg.rank, cfg.nranks = rank, world
-    if world > 1:
-        idt = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            import ctypes as C
-            buf = (C.c_uint8 * 128)()
-            assert pm.lib().pm_nccl_unique_id(buf) == 0
-            idt = torch.tensor(list(buf), dtype=torch.uint8)
-        idt = idt.cuda()
-        dist.broadcast(idt, 0)
-        for q, b in enumerate(idt.cpu().tolist()):
-            cfg.nccl_id[q] = b
-    S = pm.Solver(cfg)
-    # u, v ~ 2^-10 * U(-1,1) by global flat index; p cold-starts in the cavity.  The amplitude keeps
-    # max|f| < 1e9: with U(-1,1) at h = 1/8192 the reference's own loop test (res = 1.0 > 1e-9*max|f|,
-    # cavity-01.cpp:618,632,635) is false before the first sweep and the solver would do no work at all.
-    S.fill_random(42, 2.0 ** -10)
+
+    def make_solver(path=None):
+        cfg = bench_cfg(pm, case, nx, ny, K_ITERS, args, local, path)
+        cfg.rank, cfg.nranks = rank, world
+        if world > 1:
+            for q, b in enumerate(nccl_id_bytes(pm, dist, rank)):
+                cfg.nccl_id[q] = b
+        S_ = pm.Solver(cfg)
+        init_state(S_, case)
+        return S_
+
+    S = make_solver()
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
         S.sync()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(args.warmup):
         S.step(1)
@@ -204,10 +397,7 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     t_after = S.timing()
     assert r.iterations == K_ITERS, f"PPE stopped after {r.iterations} iterations (expected the K={K_ITERS} cap)"
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ms)
     cells = nx * ny  # all ranks
     value = cells * args.steps / (ms * 1e-3) / 1e6
 
@@ -220,13 +410,12 @@ def run_ours(args):
     ms_per_pass = ppe_ms / passes if passes else float("nan")
     achieved = bytes_per_pass / (ms_per_pass * 1e-3) / 1e9
     step_bytes = bytes_per_cell_step(K_ITERS) * nx * ny_local
-    traffic = None  # measured DRAM bytes per launch (ncu), when this exact workload was profiled
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath) and world == 1 and args.ppe == "rb" and not args.exact:
-        key = f"k_ppe_tiled<Fast,0,1,{int(round(sweeps_per_pass + 0.4))},0> {nx}x{ny}"  # same loads and stores since the first capture
-        traffic = json.load(open(tpath)).get(key, {}).get("dram_bytes_per_launch")
+    traffic, traffic_src = None, None
+    if world == 1 and args.ppe == "rb" and not args.exact:
+        traffic, traffic_src = measured_traffic(f"{case} {nx}x{ny} T={int(round(sweeps_per_pass + 0.4))}")
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+        "frac_real_traffic": (traffic / (ms_per_pass * 1e-3) / 1e9 / peak) if traffic else None,
         "kernel": "pressure sweep pass (sweep(s) + fused inf-norm residual)", "peak_source": peak_src,
         "algorithmic_bytes_per_launch": bytes_per_pass, "ms_per_launch": ms_per_pass, "sweeps_per_launch": sweeps_per_pass,
         "whole_step": {"algorithmic_GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,
@@ -234,6 +423,43 @@ def run_ours(args):
                        "frac_of_nominal_8TBps": step_bytes / (ms / args.steps * 1e-3) / 1e9 / 8000.0,
                        "bytes_per_cell_step": bytes_per_cell_step(K_ITERS)},
     }
+
+    # ---- parity of the benchmarked run: the same steps through the general path (one kernel per colour + a residual
+    # pass, itself pinned to the oracle bit for bit at oracle sizes), same inputs; every rank compares its own slab ----
+    parity = None
+    if not args.no_parity:
+        nsteps = args.warmup + args.steps
+        mine = {}
+        for f in (pm.F_U, pm.F_V, pm.F_P):
+            shp = S.slab_rows(f)[1:]
+            a = np.empty(shp, dtype=np.float64)
+            S.download_slab_ptr(f, a.ctypes.data, a.size)
+            mine[f] = a
+        G = make_solver(path=pm.PATH_SIMPLE)
+        t0 = time.perf_counter()
+        rg = G.step(nsteps)
+        G.sync()
+        g_ms = (time.perf_counter() - t0) * 1e3 / nsteps
+        worst, finite = {}, True
+        for name, f in (("u", pm.F_U), ("v", pm.F_V), ("p", pm.F_P)):
+            b = np.empty_like(mine[f])
+            G.download_slab_ptr(f, b.ctypes.data, b.size)
+            finite = finite and bool(np.isfinite(mine[f]).all()) and bool(np.isfinite(b).all())
+            scale = max_over_ranks(float(np.abs(b).max()))
+            worst[name] = max_over_ranks(float(np.abs(mine[f] - b).max())) / (scale if scale > 0 else 1.0)
+            del b
+        G.close()
+        del mine
+        finite = max_over_ranks(0.0 if finite else 1.0) == 0.0
+        parity = {"against": "general path (kernel_path=1) run of the same steps on the same inputs", "steps": nsteps,
+                  "rel_linf": worst, "finite": finite, "iterations_equal": rg.iterations == r.iterations,
+                  "residual_rel_diff": abs(rg.residual - r.residual) / rg.residual if rg.residual else 0.0,
+                  "general_path_ms_per_step": g_ms, "ok": bool(finite and max(worst.values()) <= (0.0 if args.exact else 1e-9))}
+        if world > 1:
+            ok, what = slabs_bit_equal(pm, dist, rank, world, local)
+            parity["slabs_bit_equal"] = ok
+            parity["slabs_case"] = what
+            parity["ok"] = bool(parity["ok"] and ok)
 
     # ---- e2e: the same step through the C-ABI with HOST buffers (pinned), every step's copies inside the timed region ----
     # Headline: pm_host_step_submit/run/drain, which overlap the upload of step n+1 and the download of step n-1 with
@@ -254,12 +480,7 @@ def run_ours(args):
             t0 = time.perf_counter()
             fn(n)
             barrier()
-            ms_ = (time.perf_counter() - t0) * 1e3
-            if dist is not None:
-                t = torch.tensor([ms_], dtype=torch.float64, device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms_ = float(t.item())
-            return ms_
+            return max_over_ranks((time.perf_counter() - t0) * 1e3)
 
         def serial(n):
             for _ in range(n):
@@ -291,6 +512,28 @@ def run_ours(args):
                        "copies of neighbouring steps overlap the kernels; wall clock from the first submit to the end of the last download",
                "serial": {"value": cells * s_steps / (s_ms * 1e-3) / 1e6, "ms_per_step": s_ms / s_steps, "steps": s_steps,
                           "what": "pm_upload_slab(u,v) + pm_step + pm_download_slab(u,v,p), nothing overlapped"}}
+        del host, src
+    gpu_launches = int(t_after.kernel_launches - t_before.kernel_launches)
+    S.close()
+
+    # ---- weak-scaling base: the same per-GPU slab on ONE GPU, timed in this very run (rank 0; the others wait) ----
+    weak_base = None
+    if world > 1 and not args.no_weak_base:
+        if rank == 0:
+            cfg1 = bench_cfg(pm, case, nx, ny_local, K_ITERS, args, local)
+            S1 = pm.Solver(cfg1)
+            init_state(S1, case)
+            b_ms, _ = device_timed(S1, max(3, min(args.steps, 8)), 3)
+            S1.close()
+            weak_base = {"workload": f"{case} {nx}x{ny_local} on 1 GPU (one slab of the above), same K, same kernel", "ms_per_step": b_ms,
+                         "value": nx * ny_local / b_ms / 1e3, "unit": UNIT,
+                         "efficiency_vs_this_base": (value / world) / (nx * ny_local / b_ms / 1e3)}
+        dist.barrier()
+
+    secondary = small = None
+    if rank == 0 and world == 1 and case == "cavity" and not args.no_secondary:
+        secondary = secondary_lines(pm, args, local)
+        small = small_configs(pm, local, not args.no_cpu)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -303,16 +546,20 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (splitmix64 2^-10*U(-1,1) u,v by global flat index, seed 42)",
-            "config": {"workload": workload, "ppe": f"{args.ppe}, K={K_ITERS} iterations/step (max_iters cap), residual every iteration, tolerance_factor 1e-12",
+            "config": {"workload": workload, "ppe": f"{args.ppe}, K={K_ITERS} iterations/step (max_iters cap), residual every iteration" + (", tolerance_factor 1e-12" if case == "cavity" else ""),
                        "arith": "exact (no FMA)" if args.exact else "production (FMA)",
                        "kernel_path": {0: "auto", 1: "simple", 2: "tiled"}[args.path],
                        "l2": "inputs larger than L2 (>= 537 MB per field vs 126 MB L2); no flush needed",
                        "parallelism": f"{world} j-slab(s)"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(t_after.kernel_launches - t_before.kernel_launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity_check": parity,
+            "gpu_launches": gpu_launches, "clocks": clocks,
         }
+        if weak_base is not None:
+            line["weak_base"] = weak_base
+        if secondary is not None:
+            line["secondary"] = secondary
+            line["small_configs"] = small
         emit(line)
-    S.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -341,7 +588,11 @@ def main():
     ap.add_argument("--exact", type=int, default=0)
     ap.add_argument("--path", type=int, default=0)
     ap.add_argument("--sweeps", type=int, default=0)
+    ap.add_argument("--case", default="cavity", choices=["cavity", "channel", "step"], help="which reference solver's form of the step (default: the BASELINE cavity)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-weak-base", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=1024)
     ap.add_argument("--cpu-steps", type=int, default=12)
