@@ -46,6 +46,26 @@ def test_reference_ordering_writes_identical_bytes(tmp_path, exe, case, stop):
         assert err == []
 
 
+def test_backwards_step_reference_ordering_writes_identical_bytes(tmp_path):
+    """backwards_step-01.cpp (VTKWriter with the FluidMask block and the literal "0.0" of solid cells, :87-311; log lines
+    :1054-1060): the reference needs 40 minutes for its 3072 steps, so its record is a run cut after frame 20
+    (make_vtk_golden.py --cases backwards_step --cut-s 45).  Frames 0, 10, 20, the stdout up to the export of frame 20
+    and the cap warnings of the first 20 steps (16 of them stop at 10 000 iterations: tests/golden/step_default_20.npz)
+    must be the reference's, byte for byte."""
+    import numpy as np
+    g = np.load(os.path.join(ROOT, "tests", "golden", "step_default_20.npz"))
+    capped = int((g["iters"] == 10000).sum())
+    rc, out, err = run("backwards_step", ["--ppe", "sor-lex", "--exact", "1", "--stop-after", "20"], tmp_path)
+    assert rc == 0, err
+    gold = GOLD["backwards_step"]
+    n = gold["stdout"].index("Exported VTK file: backwards_step_000020.vtk") + 1
+    assert out[:n] == gold["stdout"][:n]
+    for step in (0, 10, 20):
+        name = f"backwards_step_{step:06d}.vtk"
+        assert md5(tmp_path / "vtk_output" / name) == gold["md5"][name], name
+    assert capped == 16 and err[:capped] == gold["stderr_first"][:capped]
+
+
 def test_readme_flags_and_error_exit(tmp_path):
     rc, out, err = run("cavity", ["--Re", "100", "--Nx", "128", "--Ny", "128", "--dt", "1e-3", "--stop-after", "2", "--no-vtk"], tmp_path)
     assert rc == 0

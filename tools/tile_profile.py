@@ -17,6 +17,9 @@ S = pm.Solver(cfg)
 S.fill_random(42, 2.0 ** -10)
 S.step(1)
 S.sync()
+a, b, c = C.c_int(), C.c_int(), C.c_int()
+if pm.lib().pm_debug_tiled_occupancy(S._h, C.byref(a), C.byref(b), C.byref(c)) == 0:
+    print(f"occupancy: {a.value} CTAs/SM, max active clusters {b.value} of size {c.value} ({b.value * c.value} CTAs = {b.value * c.value / 148:.2f} per SM)")
 buf = (C.c_ulonglong * 8)()
 pm.lib().pm_debug_tile_profile(buf, 1)
 S.timer_start()
