@@ -1354,6 +1354,26 @@ extern "C" int pm_timer_stop(pm_solver* s, double* elapsed_ms) {
   return PM_OK;
 }
 
+// Measurement helper (not part of pm.h): how many CTAs / clusters of the tiled pressure kernel the device keeps resident.
+extern "C" int pm_debug_tiled_occupancy(pm_solver* s, int* ctas_per_sm, int* max_active_clusters, int* cluster_size) {
+  if (!s || !s->use_tiled) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  const TiledPlan& pl = s->tiled;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, pl.kernel, pl.threads, size_t(pl.smem_bytes)));
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(pl.tiles_x, pl.tiles_y * pl.cs);
+  lc.blockDim = dim3(pl.threads);
+  lc.dynamicSmemBytes = size_t(pl.smem_bytes);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = unsigned(pl.cs); at[0].val.clusterDim.z = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  CK(cudaOccupancyMaxActiveClusters(max_active_clusters, pl.kernel, &lc));
+  *cluster_size = pl.cs;
+  return PM_OK;
+}
+
 #ifdef PM_TILE_PROFILE
 // Debug builds only (make variant EXTRA=-DPM_TILE_PROFILE): cycles per phase of the tiled kernel, summed over CTAs.
 extern "C" int pm_debug_tile_profile(unsigned long long out[8], int reset) {

@@ -62,6 +62,41 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// ---- thread-block cluster primitives: distributed shared memory (SASS: mapa -> UMOV/PRMT on the CTA id, st.async -> STAS)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+// One double into another CTA's shared memory; its arrival is counted (8 bytes) on that CTA's mbarrier.
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+               "l"(__double_as_longlong(v)), "r"(remote_bar)
+               : "memory");
+}
+// relaxed: the arrive orders nothing itself (a release would drain every outstanding load behind a MEMBAR.GPU); the
+// barrier initialisation it announces was published by fence.mbarrier_init.release.cluster
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t phase) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(phase)
+        : "memory");
+  } while (!ok);
+}
+
 #ifdef PM_TILE_PROFILE
 // Debug build only (make variant EXTRA=-DPM_TILE_PROFILE): cycles per phase summed over the CTAs, thread 0's clock.
 __device__ unsigned long long g_tile_prof[8];
@@ -166,6 +201,72 @@ __device__ __forceinline__ double res_sum22(const KP& k, double pc, double sew, 
   return fma(-k.denom, pc, fma(k.idx2, sew, fma(k.idy2, sns, -f)));
 }
 
+// Edge-row exchange between the CTAs of a cluster (stacked in y).  After colour half-sweep h every CTA pushes the
+// cells of that colour of its first row into the row above the tile of the CTA below (tile row SH there) and of its
+// last row into the row below the tile of the CTA above (tile row -1 there), one st.async per thread and direction;
+// the 64 x 8 bytes of a half-sweep complete one phase of an mbarrier in the receiving CTA, which the threads that
+// read that row wait on before half-sweep h + 1.  Two barriers per direction, alternating with h, so a phase can never
+// receive bytes of the next one: the data of half-sweep h + 2 depends on what this CTA sends after it has waited
+// for half-sweep h.  For the same reason a row is never overwritten before its last reader is done.
+// The last half-sweep of a pass sends nothing (nobody reads it), so every byte sent is waited for before the
+// receiving CTA can finish: no cluster barrier at the end.
+// The remote addresses are re-derived from the thread's tile pointer at every use, so the exchange keeps only two flags
+// per thread across the sweeps.
+struct Xchg {
+  uint64_t* bars;  // this CTA's four mbarriers: [0..1] count bytes arriving from below, [2..3] from above
+  int nhs;         // half-sweeps of this pass
+  bool dn, up;     // this thread holds cells of the tile's first row and the CTA below exchanges / last row and the CTA above
+};
+#define PM_XCHG_BYTES 512u  // 64 cells of one colour per row
+// After half-sweep h in which the .x cell of the thread's first row was the target iff x_first: push the edge cells.
+// tpx = the thread's .x cell of its first row inside the tile; segment 0 holds the tile's first rows, segment NSEG-1 its last.
+template <class C>
+__device__ __forceinline__ void xchg_send(const Xchg& x, const double* tpx, const Cells<C::RPT>& c, bool x_first, int h) {
+  constexpr int SW = C::SW, SH = C::SH, RPT = C::RPT;
+  if (h >= x.nhs - 1) return;  // nothing follows that would read it
+  const uint32_t b = uint32_t(h & 1) * 8u;
+  if (x.dn) {  // my first row -> tile row SH of the CTA below; counted on its "from above" pair
+    const uint32_t rank = cluster_ctarank() - 1u;
+    const uint32_t row = mapa_u32(smem_u32(tpx + SH * SW), rank), rbar = mapa_u32(smem_u32(x.bars + 2), rank);
+    st_async_f64(row + (x_first ? 0u : uint32_t(SW / 2) * 8u), x_first ? c.p0[0] : c.p1[0], rbar + b);
+  }
+  if (x.up) {  // my last row -> tile row -1 of the CTA above; counted on its "from below" pair
+    const uint32_t rank = cluster_ctarank() + 1u;
+    const uint32_t row = mapa_u32(smem_u32(tpx - ((C::NSEG - 1) * RPT + 1) * SW), rank), rbar = mapa_u32(smem_u32(x.bars), rank);
+    // RPT is even: in the last row the roles of .x and .y are swapped
+    st_async_f64(row + (x_first ? uint32_t(SW / 2) * 8u : 0u), x_first ? c.p1[RPT - 1] : c.p0[RPT - 1], rbar + b);
+  }
+}
+// Once per pass, by every thread, before the first push: all CTAs of the cluster are ready to receive.
+__device__ __forceinline__ void xchg_gate(int h) {
+  if (h == 0) cluster_wait_acquire();
+}
+// Before the edge rows of half-sweep h + 1 read them: the edge cells the neighbours pushed after their half-sweep h.
+// (Tried: waits without a "memory" clobber, the guarded loads tied to a token the wait returns -- no faster, and ptxas
+// 12.9 lost the token's value on the path where the first try succeeds.)
+template <class C>
+__device__ __forceinline__ void xchg_wait(const Xchg& x, int h) {
+  if (h < 0 || !(x.dn || x.up)) return;
+  const bool lead = (threadIdx.x & 63) == 0;
+#ifdef PM_TILE_PROFILE
+  const long long w0 = clock64();
+#endif
+  const bool again = h + 2 < x.nhs - 1;  // the same barrier serves half-sweep h + 2 if that one sends
+  if (x.dn) {
+    const uint32_t bar = smem_u32(x.bars + (h & 1));
+    mbar_wait_u32(bar, uint32_t(h >> 1) & 1u);
+    if (lead && again) mbar_expect_tx_u32(bar, PM_XCHG_BYTES);
+  }
+  if (x.up) {
+    const uint32_t bar = smem_u32(x.bars + 2 + (h & 1));
+    mbar_wait_u32(bar, uint32_t(h >> 1) & 1u);
+    if (lead && again) mbar_expect_tx_u32(bar, PM_XCHG_BYTES);
+  }
+#ifdef PM_TILE_PROFILE
+  if (lead) atomicAdd(&g_tile_prof[6], (unsigned long long)(clock64() - w0));  // summed over both edge segments
+#endif
+}
+
 // Shared-memory layout of the exchange tile ("split rows"): within each 128-double row the 64 even columns
 // come first, then the 64 odd ones: column c lives at (c & 1) * 64 + (c >> 1).  Lane q of a warp owns columns
 // 2q (.x) and 2q+1 (.y); its west neighbour 2q-1 and east neighbour 2q+2 then sit at consecutive doubles
@@ -267,12 +368,11 @@ __device__ __forceinline__ void rb_half(const KP& k, double* tpx, double* tpy, C
 // The iterates differ from the reference trees by rounding only (exact_arith = 1 keeps the trees).
 template <int FORM, class C, int PX, bool PRE>
 __device__ __forceinline__ void rb_half_lean(const KP& k, double* tpx, double* tpy, Cells<C::RPT>& c, unsigned mOut,
-                                             double& rmax_pre, double& rmax_post) {
+                                             double& rmax_pre, double& rmax_post, const Xchg& x, int h) {
   constexpr int SW = C::SW, RPT = C::RPT;
   static_assert(RPT % 2 == 0, "rows are processed in pairs");
   double mx = PRE ? rmax_pre : 0.0;
-#pragma unroll
-  for (int a = 0; a < RPT; a += 2) {
+  auto row_pair = [&](const int a) {
     const int b = a + 1;
     // row a: target tA (.x iff PX == 0); row b: the other column
     double rA, rB;
@@ -315,6 +415,21 @@ __device__ __forceinline__ void rb_half_lean(const KP& k, double* tpx, double* t
       acc_max(mx, rA, (mOut >> (16 + a)) & 1u);
       acc_max(mx, rB, (mOut >> b) & 1u);
     }
+  };
+  if (C::CS > 1) {
+    // The thread's first and last row LAST: what they read from the neighbour CTAs was pushed at the end of the previous
+    // half-sweep and has had this half-sweep's inner rows to arrive in; their new values leave right away and have the
+    // neighbours' inner rows of the next half-sweep to travel.
+#pragma unroll
+    for (int a = 2; a < RPT - 2; a += 2) row_pair(a);
+    xchg_wait<C>(x, h - 1);
+    row_pair(0);
+    if (RPT > 2) row_pair(RPT - 2);
+    xchg_gate(h);
+    xchg_send<C>(x, tpx, c, PX == 0, h);
+  } else {
+#pragma unroll
+    for (int a = 0; a < RPT; a += 2) row_pair(a);
   }
   if (PRE) rmax_pre = mx;
   else {
@@ -405,27 +520,33 @@ __device__ __forceinline__ void jacobi_sweep(const KP& k, double* tpx, double* t
 template <class A, int FORM, int METHOD, int T, bool INT, int PAR0>
 __device__ __forceinline__ void run_sweeps(const KP& k, double* tpx, double* tpy, Cells<TileCfg<METHOD, T>::RPT>& c, int i0, int jg0,
                                            unsigned mW, unsigned mOut, bool colW0, bool colW1, int nsw,
-                                           unsigned long long* __restrict__ red) {
+                                           unsigned long long* __restrict__ red, const Xchg& x) {
   using C = TileCfg<METHOD, T>;
+  constexpr bool XC = C::CS > 1;
   const int lane = threadIdx.x & 31;
   unsigned long long* redw = red + (threadIdx.x >> 5) * (T + 1);
   double r_cur = 0.0, r_next = 0.0;  // residual maxima of iterate m0+t and m0+t+1
   const int nloop = nsw > 0 ? nsw : 1;
+  if (XC && nsw == 0) cluster_wait_acquire();  // the residual-only pass pushes nothing; complete the barrier all the same
 #pragma unroll 1
   for (int t = 0; t < nloop; ++t) {
     const bool commit = t < nsw;
     if (METHOD == PM_PPE_SOR_RB) {
       // colour 0 first ((i + j) even), as the oracle's red-black restatement
       if (INT && !A::exact) {  // interior tiles are only run with nsw > 0: commit is always true here
-        rb_half_lean<FORM, C, PAR0, true>(k, tpx, tpy, c, mOut, r_cur, r_next);
+        rb_half_lean<FORM, C, PAR0, true>(k, tpx, tpy, c, mOut, r_cur, r_next, x, 2 * t);
         __syncthreads();
-        rb_half_lean<FORM, C, 1 - PAR0, false>(k, tpx, tpy, c, mOut, r_cur, r_next);
+        rb_half_lean<FORM, C, 1 - PAR0, false>(k, tpx, tpy, c, mOut, r_cur, r_next, x, 2 * t + 1);
         __syncthreads();
       } else {
+        if (XC) xchg_wait<C>(x, 2 * t - 1);
         rb_half<A, FORM, INT, C, PAR0, true, false>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, commit, r_cur, r_next);
         if (commit) {
+          if (XC) { xchg_gate(2 * t); xchg_send<C>(x, tpx, c, PAR0 == 0, 2 * t); }
           __syncthreads();
+          if (XC) xchg_wait<C>(x, 2 * t);
           rb_half<A, FORM, INT, C, 1 - PAR0, false, true>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, true, r_cur, r_next);
+          if (XC) xchg_send<C>(x, tpx, c, PAR0 == 1, 2 * t + 1);
           __syncthreads();
         }
       }
@@ -467,15 +588,19 @@ template <class A, int FORM, int METHOD, int T, int PAR0>
 __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t* bar, uint32_t phase, unsigned long long* red,
                                              double* __restrict__ pout, const double* __restrict__ f, PpeState* __restrict__ st,
                                              unsigned long long* __restrict__ res_bits, unsigned long long* __restrict__ fold_part, int m0, int nsw, int bx, int by,
-                                             const StopWords<T>& stopw, bool check_stop) {
+                                             int crank, uint64_t* xbar, const int* xact, const StopWords<T>& stopw, bool check_stop) {
   using C = TileCfg<METHOD, T>;
-  constexpr int H = C::H, SW = C::SW, SH = C::SH, RPT = C::RPT, TX = C::TX, TY = C::TY;
+  constexpr int H = C::H, SW = C::SW, SH = C::SH, RPT = C::RPT, TX = C::TX, TY = C::TY, CS = C::CS;
   const int tid = threadIdx.x;
 #ifdef PM_TILE_PROFILE
   long long prof_t = clock64();
 #endif
+  // (bx, by) = the cluster's output block; CTA `crank` of the cluster holds tile rows crank*SH .. crank*SH + SH-1 of
+  // the cluster's (CS*SH) x SW tile.  Only the two ends of the stack have ring rows in y.
+  const bool has_dn = crank > 0, has_up = crank < CS - 1;
   const int x0 = 1 + bx * TX, y0 = 1 + by * TY;  // first output cell (i, jl)
-  const int ib = x0 - H, jb = y0 - H;            // tile origin (i, jl)
+  const int ib = x0 - H, jb = y0 - H + crank * SH;  // this CTA's tile origin (i, jl)
+  const int out_lo = has_dn ? 0 : H, out_hi = has_up ? SH - 1 : SH - H - 1;  // tile rows that belong to the output block
   const int q = tid & 63, sg = tid >> 6;
   const int c0 = 2 * q, i0 = ib + c0;
   const int rr0 = sg * RPT;
@@ -484,7 +609,7 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
   const bool colW0 = colI0 && c0 >= 1, colW1 = colI1 && c0 + 1 <= SW - 2;
   const bool colO0 = colI0 && c0 >= H && c0 < H + TX, colO1 = colI1 && c0 + 1 >= H && c0 + 1 < H + TX;
   // Row masks as bit ranges over the thread's RPT rows (bit r = row rr0 + r):
-  //   mI: the row holds domain cells this rank has data for;  mW: ... and is not a ring row of the tile;
+  //   mI: the row holds domain cells this rank has data for;  mW: ... and is not a ring row of the cluster's tile;
   //   mO: the row belongs to the output block and to this rank.
   auto bit_range = [](int lo, int hi) -> unsigned {  // bits lo..hi of an RPT-bit mask, empty if hi < lo
     lo = max(lo, 0);
@@ -493,12 +618,13 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
   };
   const int jI_lo = max(1 - k.j0, 1 - H), jI_hi = min(k.ny - k.j0, k.nyl + H);  // jl range with data
   const unsigned mI = bit_range(jI_lo - jl0, jI_hi - jl0);
-  const unsigned mW = mI & bit_range(1 - rr0, SH - 2 - rr0);
-  const unsigned mO = bit_range(max(1 - jl0, H - rr0), min(k.nyl - jl0, H + TY - 1 - rr0));
+  const int w_lo = has_dn ? 0 : 1, w_hi = has_up ? SH - 1 : SH - 2;  // tile rows that may be updated
+  const unsigned mW = mI & bit_range(w_lo - rr0, w_hi - rr0);
+  const unsigned mO = bit_range(max(1 - jl0, out_lo - rr0), min(k.nyl - jl0, out_hi - rr0));
   const unsigned mOut = (colO0 ? mO : 0u) | ((colO1 ? mO : 0u) << 16);
-  // Every updatable cell of the tile strictly inside the domain (uniform over the block)?
-  const bool interior = ib + 1 >= 2 && ib + SW - 2 <= k.nx - 1 && k.j0 + jb + 1 >= 2 && k.j0 + jb + SH - 2 <= k.ny - 1 &&
-                        jb + SH - 1 <= k.nyl + H;
+  // Every updatable cell of the tile strictly inside the domain, with data for all of its neighbours (uniform over the block)?
+  const bool interior = ib + 1 >= 2 && ib + SW - 2 <= k.nx - 1 && k.j0 + jb + w_lo >= 2 && k.j0 + jb + w_hi <= k.ny - 1 &&
+                        jb + w_hi + 1 <= k.nyl + H;
   if (tid < C::NWARPS * (T + 1)) red[tid] = 0ull;  // ordered before the warps' stores by the barriers below
 
   // f: HBM -> registers, 128-bit row loads, overlapping the TMA transfer of p
@@ -534,10 +660,14 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
         st->done = 1;
       }
       mbar_wait(bar, phase);  // never leave with a bulk copy still landing in this CTA's shared memory
+      if (CS > 1) { cluster_arrive_relaxed(); cluster_wait_acquire(); }  // no CTA of the cluster is left waiting for this one
       return;
     }
   }
   mbar_wait(bar, phase);
+  // Cluster barrier, first half: this CTA's barriers are initialised and its tile (with the rows the neighbours will
+  // overwrite) has landed.  Second half: before the first push into a neighbour (xchg_gate).
+  if (CS > 1) cluster_arrive_relaxed();
   PM_PROF(1);  // wait for the TMA tile
   // The tile arrived in the split-row layout: every thread takes its own cells; neighbours are read in place.
   // No barrier: before the first half-sweep's barrier a thread only ever writes cells it owns.
@@ -550,9 +680,14 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
   }
 
   PM_PROF(2);  // own cells
+  Xchg x;
+  x.bars = xbar;
+  x.nhs = 2 * nsw;
+  x.dn = CS > 1 && sg == 0 && xact[0];
+  x.up = CS > 1 && sg == C::NSEG - 1 && xact[1];
   // the residual-only pass (nsw == 0) commits nothing and takes the general code path
-  if (interior && nsw > 0) run_sweeps<A, FORM, METHOD, T, true, PAR0>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red);
-  else run_sweeps<A, FORM, METHOD, T, false, PAR0>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red);
+  if (interior && nsw > 0) run_sweeps<A, FORM, METHOD, T, true, PAR0>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red, x);
+  else run_sweeps<A, FORM, METHOD, T, false, PAR0>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red, x);
 
   PM_PROF(3);  // the sweeps
   // ---- write the output block (split-row layout: .x cells to the even half of the row, .y cells to the odd
@@ -599,22 +734,28 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
 #endif
 }
 
-// One tile per CTA, two CTAs per SM: one CTA's loads overlap the other's sweeps.
+// One tile per CTA, two CTAs per SM: one CTA's loads overlap the other's sweeps.  Red-black: CS CTAs stacked in y
+// form a cluster (launch attribute), blockIdx.y = cluster row * CS + rank in the cluster.
 template <class A, int FORM, int METHOD, int T, int PAR0>
 __global__ void __launch_bounds__((TileCfg<METHOD, T>::THREADS), PM_TILE_MINBLOCKS)
     k_ppe_tiled(const __grid_constant__ KP k, const __grid_constant__ CUtensorMap tmap_in, double* __restrict__ pout,
                 const double* __restrict__ f, PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits,
                 unsigned long long* __restrict__ fold_part, int m0, int nsw, int force, int tile_row0) {
   using C = TileCfg<METHOD, T>;
+  constexpr int CS = C::CS;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  double* tile = reinterpret_cast<double*>(smem_raw) + C::SW;  // one spare row above (and one below)
+  double* tile = reinterpret_cast<double*>(smem_raw) + C::SW;  // tile rows -1 .. SH: the row below and above come along
   __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(16) uint64_t xbar[4];  // edge rows from the CTA below [0..1] / above [2..3], alternating with the half-sweep
+  __shared__ int xact[2];                     // does this CTA exchange edge rows with the CTA below [0] / above [1]
   __shared__ unsigned long long red[C::NWARPS * (T + 1)];  // per warp: bit patterns of the residual maxima of iterates m0 .. m0+T
 
   const int tid = threadIdx.x;
-  // tile rows rotated by one: the last row of the launch (all boundary tiles at the top wall, several times
+  // cluster rows rotated by one: the last row of the launch (all boundary tiles at the top wall, several times
   // slower than interior tiles) starts in the first wave instead of forming the tail
-  const int bx = blockIdx.x, by = tile_row0 + (blockIdx.y == 0 ? int(gridDim.y) - 1 : int(blockIdx.y) - 1);
+  const int ncy = int(gridDim.y) / CS, cy = int(blockIdx.y) / CS;
+  const int crank = CS > 1 ? int(cluster_ctarank()) : 0;
+  const int bx = blockIdx.x, by = tile_row0 + (cy == 0 ? ncy - 1 : cy - 1);
 #ifdef PM_TILE_PROFILE
   const long long prof_k = clock64();
 #endif
@@ -622,9 +763,31 @@ __global__ void __launch_bounds__((TileCfg<METHOD, T>::THREADS), PM_TILE_MINBLOC
   // independent loads and are looked at only after the f loads of the tile have been issued.
   if (tid == 0) {
     mbar_init(&mbar, 1);
+    if (CS > 1) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) mbar_init(&xbar[b], 1);
+    }
     fence_mbar_init();
-    mbar_expect_tx(&mbar, C::SH * C::SW * 8);
-    tma_load_3d(tile, &tmap_in, &mbar, (PM_OFFC + 1 + bx * C::TX - C::H + k.psh) >> 1, 0, k.padr + 1 + by * C::TY - C::H);
+    mbar_expect_tx(&mbar, (C::SH + 2 * C::XR) * C::SW * 8);
+    tma_load_3d(tile - C::XR * C::SW, &tmap_in, &mbar, (PM_OFFC + 1 + bx * C::TX - C::H + k.psh) >> 1, 0,
+                k.padr + 1 + by * C::TY - C::H + crank * C::SH - C::XR);
+    if (CS > 1) {
+      // A pair of stacked CTAs exchanges only where both edge rows are interior rows of the domain: a wall ghost row is
+      // kept up to date inside the tile by the thread that owns the wall-adjacent cell (FORM 1) or never changes (FORM 0).
+      const int j_first = k.j0 + 1 + by * C::TY - C::H + crank * C::SH, j_last = j_first + C::SH - 1;
+      xact[0] = crank > 0 && j_first - 1 >= 1 && j_first <= k.ny;
+      xact[1] = crank < CS - 1 && j_last >= 1 && j_last + 1 <= k.ny;
+      // arm the phases of half-sweeps 0 and 1 where a neighbour will send (the last half-sweep of a pass sends nothing)
+      const int nhs = 2 * nsw;
+      if (crank > 0) {
+        if (0 < nhs - 1) mbar_expect_tx(&xbar[0], PM_XCHG_BYTES);
+        if (1 < nhs - 1) mbar_expect_tx(&xbar[1], PM_XCHG_BYTES);
+      }
+      if (crank < CS - 1) {
+        if (0 < nhs - 1) mbar_expect_tx(&xbar[2], PM_XCHG_BYTES);
+        if (1 < nhs - 1) mbar_expect_tx(&xbar[3], PM_XCHG_BYTES);
+      }
+    }
   }
   StopWords<T> stopw;
   if (!force) stopw = stop_words_load<T>(st, res_bits, m0);
@@ -632,7 +795,7 @@ __global__ void __launch_bounds__((TileCfg<METHOD, T>::THREADS), PM_TILE_MINBLOC
 #ifdef PM_TILE_PROFILE
   if (tid == 0) atomicAdd(&g_tile_prof[5], (unsigned long long)(clock64() - prof_k));
 #endif
-  tile_process<A, FORM, METHOD, T, PAR0>(k, tile, &mbar, 0u, red, pout, f, st, res_bits, fold_part, m0, nsw, bx, by, stopw, !force);
+  tile_process<A, FORM, METHOD, T, PAR0>(k, tile, &mbar, 0u, red, pout, f, st, res_bits, fold_part, m0, nsw, bx, by, crank, xbar, xact, stopw, !force);
 }
 
 // Whole-plane conversion between the natural and the split-row layout (a permutation inside every row).
@@ -662,7 +825,9 @@ struct TiledPlan {
   int halo = 2;         // H
   int tx = 0, ty = 0;   // output block
   int sh = 0, threads = 0;  // tile rows, threads per CTA
-  int tiles_x = 0, tiles_y = 0;
+  int tiles_x = 0, tiles_y = 0;  // output blocks; in y one block per CLUSTER of cs stacked CTAs
+  int cs = 1;                    // CTAs per cluster
+  int box_rows = 0;              // rows of the TMA box: the tile, plus the row below and above it in a cluster
   int smem_bytes = 0;
   int psh = 0;          // column shift of the split-row layout (KP::psh)
   CUtensorMap map[2];   // p ping / p pong
@@ -692,7 +857,7 @@ template <int METHOD, int T>
 static void tiled_geometry(TiledPlan* pl) {
   using C = TileCfg<METHOD, T>;
   pl->sweeps = T; pl->halo = C::H; pl->tx = C::TX; pl->ty = C::TY; pl->sh = C::SH; pl->threads = C::THREADS;
-  pl->smem_bytes = C::SMEM_BYTES; pl->psh = C::PSH;
+  pl->smem_bytes = C::SMEM_BYTES; pl->psh = C::PSH; pl->cs = C::CS; pl->box_rows = C::SH + 2 * C::XR;
 }
 
 template <class A, int FORM>
@@ -736,7 +901,7 @@ static inline bool tiled_create(TiledPlan* pl, const pm_config& c, const KP& k, 
   for (int b = 0; b < 2; ++b) {  // {pair, parity, row} view of a split-row plane
     const cuuint64_t gdim[3] = {cuuint64_t(k.pitch / 2), 2u, cuuint64_t(rows_alloc)};
     const cuuint64_t gstr[2] = {cuuint64_t(k.pitch / 2) * 8, cuuint64_t(k.pitch) * 8};
-    const cuuint32_t box[3] = {64u, 2u, cuuint32_t(pl->sh)};
+    const cuuint32_t box[3] = {64u, 2u, cuuint32_t(pl->box_rows)};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = encode(&pl->map[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, pl->p[b], gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -764,7 +929,17 @@ static inline cudaError_t tiled_launch(const TiledPlan* pl, const KP& k, int in,
   double* pout = pl->p[in ^ 1];
   void* args[] = {(void*)&k, (void*)&pl->map[in], (void*)&pout, (void*)&f, (void*)&st, (void*)&res, (void*)&pl->fold_part,
                   (void*)&m0, (void*)&nsw, (void*)&force, (void*)&tile_row0};
-  return cudaLaunchKernel(pl->kernel, dim3(pl->tiles_x, tile_rows), dim3(pl->threads), args, size_t(pl->smem_bytes), stream);
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(pl->tiles_x, tile_rows * pl->cs);
+  lc.blockDim = dim3(pl->threads);
+  lc.dynamicSmemBytes = size_t(pl->smem_bytes);
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = unsigned(pl->cs); at[0].val.clusterDim.z = 1;
+  lc.attrs = at;
+  lc.numAttrs = pl->cs > 1 ? 1 : 0;
+  return cudaLaunchKernelExC(&lc, pl->kernel, args);
 }
 // Behind all launches of the pass that started at iterate m0 with nsw sweeps.
 static inline cudaError_t tiled_fold_launch(const TiledPlan* pl, const KP& k, unsigned long long* res, int m0, int nsw, cudaStream_t stream) {

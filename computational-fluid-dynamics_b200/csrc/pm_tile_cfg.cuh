@@ -22,6 +22,15 @@
 #ifndef PM_TILE_MINBLOCKS
 #define PM_TILE_MINBLOCKS 2
 #endif
+// Red-black tiles can be stacked into thread-block clusters of PM_TILE_CS CTAs in y: the CTAs of a stack exchange their
+// edge rows through distributed shared memory after every colour half-sweep, so only the two ends of the stack carry
+// a halo in y.  At T = 4 (halo 8) the share of output cells goes from 58 % (one 48 x 128 tile) to 80 % (four).
+// Measured at 8192^2: the 27 % fewer cell updates are eaten by the lock step of the stack (a CTA's half-sweep
+// grows from 1060 to 1500-1700 cycles): 13.8 ms/step either way.  Default 1 (independent tiles); lib/libpm_cs4.so is the
+// cluster build the GPU tests also run.
+#ifndef PM_TILE_CS
+#define PM_TILE_CS 1
+#endif
 
 template <int METHOD, int T>
 struct TileCfg {
@@ -32,10 +41,13 @@ struct TileCfg {
   static constexpr int THREADS = 64 * NSEG;
   static constexpr int NWARPS = THREADS / 32;
   static constexpr int SH = NSEG * RPT;           // tile height
-  static constexpr int TX = SW - 2 * H;           // output block
-  static constexpr int TY = SH - 2 * H;
-  static constexpr int SMEM_BYTES = (SH + 2) * SW * 8;  // tile + one spare row above and below
+  static constexpr int CS = (METHOD == PM_PPE_SOR_RB) ? PM_TILE_CS : 1;  // CTAs per cluster (stacked in y)
+  static constexpr int TX = SW - 2 * H;           // output block of a cluster
+  static constexpr int TY = CS * SH - 2 * H;
+  static constexpr int XR = CS > 1 ? 1 : 0;       // rows below and above the tile that the TMA load brings along (the neighbour CTAs' edge rows)
+  static constexpr int SMEM_BYTES = (SH + 2) * SW * 8;  // tile + one row above and below (the neighbour CTA's edge row, or spare)
   static_assert(TX > 0 && TY > 0, "halo too deep for the tile");
+  static_assert(CS >= 1 && CS <= 8, "portable cluster sizes only");
   static_assert(RPT % 2 == 0 && TY % 2 == 0, "PAR0 (colour of a thread's first row) must not depend on the segment or the tile row");
   static_assert(H <= PM_PADR, "halo deeper than the pad rows of the planes");
   static_assert(H % 2 == 0 && TX % 4 == 0 && (PM_OFFC + 1) % 2 == 0 && PM_OFFC + 1 >= H,

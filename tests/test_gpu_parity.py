@@ -309,6 +309,24 @@ def test_tiled_stopping_rule_bit_exact(pm, orc, case_id, nx, ny, T, steps):
     assert_fields_equal(S, O, range(6), "tiled whole steps")
 
 
+def test_cluster_build_bit_exact():
+    """lib/libpm_cs4.so: the same sources with the red-black tiles stacked into thread-block clusters of four CTAs that
+    push their edge rows into each other's shared memory after every colour half-sweep (st.async + mbarrier; DSMEM).
+    The tiled parity tests above (0 ulp against the oracle, stopping rule, production arithmetic, ragged grids) are run
+    again in a child process bound to that library."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "computational-fluid-dynamics_b200", "lib", "libpm_cs4.so")
+    assert os.path.exists(lib), "lib/libpm_cs4.so not built (make -C computational-fluid-dynamics_b200)"
+    env = dict(os.environ, PM_LIB=lib)
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                          "tiled_ppe_bit_exact or tiled_production or tiled_stopping or ragged or auto_path"],
+                         env=env, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+
+
 @pytest.mark.parametrize("exact", [1, 0])
 def test_large_grid_8192_tiled_equals_general_path(pm, exact):
     """BASELINE configs[3] size, where the oracle is too slow: with exact arithmetic the tiled path must give

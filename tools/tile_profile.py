@@ -31,5 +31,6 @@ names = ["masks + f loads issued", "wait for the TMA tile", "own cells out of th
 names.append("kernel entry: mbarrier, TMA issue, loop-test loads, barrier")
 tot = sum(buf[q] for q in range(6))
 print(f"{n}x{n}: {ms / 2:.2f} ms/step, {ctas} tile CTAs, {tot / ctas:.0f} cycles per CTA")
+print(f"  (inside the sweeps) waiting for the neighbour CTAs' edge rows, lead threads of the two edge segments together: {buf[6] / ctas:9.0f} cycles per CTA")
 for q, nm in enumerate(names):
     print(f"  {nm:45s} {buf[q] / ctas:9.0f} cycles  {100.0 * buf[q] / tot:5.1f} %")
