@@ -213,10 +213,16 @@ static int upload_mask_rows(pm_solver* s, const uint8_t* global_mask) {
     for (int i = 1; i <= k.nx; ++i) cnt += global_mask[size_t(j) * cols + i] ? 1 : 0;
   s->kp.fluid_count_global = cnt;
   CK(cudaMemsetAsync(s->mask, 0, s->plane, s->stream));
-  // local rows 0..nyl+1 <- global rows j0..j0+nyl+1
-  CK(cudaMemcpy2DAsync(s->mask + pm_idx(k, 0, 0), size_t(k.pitch), global_mask + size_t(k.j0) * cols, size_t(cols),
-                       size_t(cols), size_t(k.nyl + 2), cudaMemcpyHostToDevice, s->stream));
+  // local rows as deep as the pad rows reach (the tiled solve looks PM_PADR rows into the neighbour slabs) <- global rows j0 + jl
+  const int jl_lo = std::max(-k.padr, -k.j0), jl_hi = std::min(k.nyl + 1 + k.padr, k.ny + 1 - k.j0);
+  CK(cudaMemcpy2DAsync(s->mask + size_t(k.padr + jl_lo) * size_t(k.pitch) + PM_OFFC, size_t(k.pitch), global_mask + size_t(k.j0 + jl_lo) * cols, size_t(cols),
+                       size_t(cols), size_t(jl_hi - jl_lo + 1), cudaMemcpyHostToDevice, s->stream));
   CK(cudaStreamSynchronize(s->stream));
+  if (s->use_tiled && k.has_mask) {
+    std::string e;
+    if (!tiled_classify(&s->tiled, k, global_mask, s->stream, &e)) return fail(s, PM_ERR_CUDA, "%s", e.c_str());
+    s->tiled.mask = s->mask;
+  }
   return PM_OK;
 }
 
@@ -299,22 +305,12 @@ static int create_impl(pm_solver* s, const pm_config* cfg) {
   CK(cudaMallocHost(&s->h_state, sizeof(PpeState)));
   CK(cudaMallocHost(&s->h_res, size_t(c.max_iters + 2) * sizeof(unsigned long long)));
 
-  // is_fluid: interior true; step: the reference rectangle (backwards_step-01.cpp:500-520)
-  {
-    std::vector<uint8_t> m(size_t(c.ny + 2) * (c.nx + 2), 0);
-    for (int j = 1; j <= c.ny; ++j)
-      for (int i = 1; i <= c.nx; ++i)
-        m[size_t(j) * (c.nx + 2) + i] =
-            (c.case_id != PM_CASE_STEP) || (i > c.step_i_location) || (j <= c.inlet_j_max) ? 1 : 0;
-    PMTRY(upload_mask_rows(s, m.data()));
-  }
-
   // kernel path.  AUTO: small grids -> the persistent cluster / single-CTA solve; every other unmasked
   // Jacobi / red-black problem -> the TMA-tiled kernel; the rest (obstacle mask beyond the small-grid limit)
   // -> the general kernels.
   const bool tiled_ok = tiled_supported(c, k);
   if (c.kernel_path == PM_PATH_TILED && !tiled_ok)
-    return fail(s, PM_ERR_UNSUPPORTED, "tiled path supports unmasked jacobi / sor-rb only");
+    return fail(s, PM_ERR_UNSUPPORTED, "tiled path: jacobi / sor-rb (with the obstacle mask: sor-rb only)");
   const size_t pbytes = size_t(c.ny + 2) * size_t(c.nx + 2) * sizeof(double);
   const bool small_ok = c.nranks == 1 && c.ppe_method != PM_PPE_SOR_LEX && pbytes <= size_t(200) * 1024 &&
                         size_t(c.nx) * size_t(c.ny) <= size_t(20) * 1024;
@@ -331,8 +327,19 @@ static int create_impl(pm_solver* s, const pm_config* cfg) {
     s->tp[1] = s->tp[0] + s->plane;
     if (!tiled_create(&s->tiled, c, k, s->tp[0], s->tp[1], s->rows_alloc, &e))
       return fail(s, PM_ERR_CUDA, "tiled path setup: %s", e.c_str());
-    s->sweeps = s->tiled.sweeps;
+    s->sweeps = s->tiled.run;
     s->kp.psh = s->tiled.psh;
+  }
+
+  // is_fluid: interior true; step: the reference rectangle (backwards_step-01.cpp:500-520).  After the kernel path is
+  // known: the tiled solve also wants the class of every tile (fluid only / solid only / both).
+  {
+    std::vector<uint8_t> m(size_t(c.ny + 2) * (c.nx + 2), 0);
+    for (int j = 1; j <= c.ny; ++j)
+      for (int i = 1; i <= c.nx; ++i)
+        m[size_t(j) * (c.nx + 2) + i] =
+            (c.case_id != PM_CASE_STEP) || (i > c.step_i_location) || (j <= c.inlet_j_max) ? 1 : 0;
+    PMTRY(upload_mask_rows(s, m.data()));
   }
 
   if (c.nranks > 1) {
@@ -756,10 +763,10 @@ static int launch_iteration_simple(pm_solver* s, int krel, int kabs) {
     k_jacobi<A, FORM><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, src, dst, f, s->mask, s->d_state, s->d_res, krel, fuse);
     CKL(s);
     if (masked) {
-      k_pghost_walls<<<(std::max(k.nx, k.nyl) + 255) / 256, 256, 0, s->stream>>>(k, dst, s->d_state, s->d_res, krel);
+      k_pghost_walls<<<(std::max(k.nx, k.nyl) + 255) / 256, 256, 0, s->stream>>>(k, dst, s->d_state, s->d_res, krel, 0, 1);
       CKL(s);
       PMTRY(exchange_halo1(s, dst));  // a solid cell in my edge row extrapolates from the neighbour slab's fresh fluid values
-      k_pghost_solid<<<cell_grid(k), cell_block(), 0, s->stream>>>(k, dst, s->mask, s->d_state, s->d_res, krel);
+      k_pghost_solid<<<cell_grid(k), cell_block(), 0, s->stream>>>(k, dst, s->mask, s->d_state, s->d_res, krel, 0, 1);
       CKL(s);
     }
     PMTRY(exchange_halo1(s, dst));
@@ -774,10 +781,10 @@ static int launch_iteration_simple(pm_solver* s, int krel, int kabs) {
     k_rb_colour<A, FORM><<<half_grid(k), cell_block(), 0, s->stream>>>(k, p, f, s->mask, s->d_state, s->d_res, krel, 1, 0, fuse);
     CKL(s);
     if (masked) {
-      k_pghost_walls<<<(std::max(k.nx, k.nyl) + 255) / 256, 256, 0, s->stream>>>(k, p, s->d_state, s->d_res, krel);
+      k_pghost_walls<<<(std::max(k.nx, k.nyl) + 255) / 256, 256, 0, s->stream>>>(k, p, s->d_state, s->d_res, krel, 0, 1);
       CKL(s);
       PMTRY(exchange_halo1(s, p));  // a solid cell in my edge row extrapolates from the neighbour slab's fresh fluid values
-      k_pghost_solid<<<cell_grid(k), cell_block(), 0, s->stream>>>(k, p, s->mask, s->d_state, s->d_res, krel);
+      k_pghost_solid<<<cell_grid(k), cell_block(), 0, s->stream>>>(k, p, s->mask, s->d_state, s->d_res, krel, 0, 1);
       CKL(s);
     }
     PMTRY(exchange_halo1(s, p));
@@ -853,7 +860,7 @@ static int tiled_pass(pm_solver* s, int in, int m0, int nsw, int force) {
 
 static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
   const TiledPlan& pl = s->tiled;
-  const int K = s->cfg.max_iters, T = pl.sweeps;
+  const int K = s->cfg.max_iters, T = pl.run;  // sweeps per pass
   const int in0 = s->tp_cur;
   CK(tiled_begin_solve(&pl, s->stream));
   if (s->cfg.nranks > 1) {  // halos of the inputs: f once per solve, p as deep as one pass reaches
@@ -1103,6 +1110,17 @@ extern "C" int pm_ppe_solve(pm_solver* s, pm_ppe_result* out) {
     PMTRY(lex_solve(s, &iters, &res));
   } else if (s->use_tiled) {
     PMTRY(tiled_solve(s, &iters, &res));
+    if (k.has_mask && iters >= 1 && std::getenv("PM_DEBUG_NO_FIXUP") == nullptr) {
+      // The tiled solve leaves the solid cells one applyPressureGhosts behind (pm_kernels_tiled.cuh, masked_tile): apply the
+      // last one to the final iterate, in the reference's order -- wall ghosts, then the solid cells (backwards_step-01.cpp:685-740).
+      double* p = s->tp[s->tp_cur];
+      k_pghost_walls<<<(std::max(k.nx, k.nyl) + 255) / 256, 256, 0, s->stream>>>(k, p, s->d_state, s->d_res, 0, 1, 0);
+      CKL(s);
+      PMTRY(exchange_halo1(s, p));
+      k_pghost_solid<<<cell_grid(k), cell_block(), 0, s->stream>>>(k, p, s->mask, s->d_state, s->d_res, 0, 1, 0);
+      CKL(s);
+      PMTRY(exchange_halo1(s, p));
+    }
   } else if (s->use_small) {
     PMTRY(small_solve(s, &iters, &res));
   } else {

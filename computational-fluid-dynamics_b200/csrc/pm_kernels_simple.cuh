@@ -515,23 +515,26 @@ __global__ void __launch_bounds__(PM_BX* PM_BY)
 
 // k8 (mask case): wall ghosts as their own pass, then solid-cell extrapolation
 // (backwards_step-01.cpp:685-740).  The wall ghosts read the pre-extrapolation values.
+// split: p is a buffer of the tiled solve (split-row layout); gated: part of the iteration loop (skipped once the
+// reference's loop test has ended it) -- the tiled solve calls both kernels once, ungated, behind its last pass.
 __global__ void k_pghost_walls(const __grid_constant__ KP k, double* __restrict__ p, PpeState* __restrict__ st,
-                               const unsigned long long* __restrict__ res_bits, int kiter_rel) {
-  if (ppe_stop_before(st, res_bits, st->kbase + kiter_rel, k.max_iters)) return;
+                               const unsigned long long* __restrict__ res_bits, int kiter_rel, int split, int gated) {
+  if (gated && ppe_stop_before(st, res_bits, st->kbase + kiter_rel, k.max_iters)) return;
   const int t = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  auto at = [&](int jl, int i) -> double& { return p[split ? pm_sidx(k, jl, i) : pm_idx(k, jl, i)]; };
   if (t <= k.nyl) {
-    p[pm_idx(k, t, 0)] = p[pm_idx(k, t, 1)];
-    p[pm_idx(k, t, k.nx + 1)] = 0.0;
+    at(t, 0) = at(t, 1);
+    at(t, k.nx + 1) = 0.0;
   }
   if (t <= k.nx) {
-    if (k.first_rank) p[pm_idx(k, 0, t)] = p[pm_idx(k, 1, t)];
-    if (k.last_rank) p[pm_idx(k, k.nyl + 1, t)] = p[pm_idx(k, k.nyl, t)];
+    if (k.first_rank) at(0, t) = at(1, t);
+    if (k.last_rank) at(k.nyl + 1, t) = at(k.nyl, t);
   }
 }
 __global__ void __launch_bounds__(PM_BX* PM_BY)
     k_pghost_solid(const __grid_constant__ KP k, double* __restrict__ p, const uint8_t* __restrict__ M,
-                   PpeState* __restrict__ st, const unsigned long long* __restrict__ res_bits, int kiter_rel) {
-  if (ppe_stop_before(st, res_bits, st->kbase + kiter_rel, k.max_iters)) return;
+                   PpeState* __restrict__ st, const unsigned long long* __restrict__ res_bits, int kiter_rel, int split, int gated) {
+  if (gated && ppe_stop_before(st, res_bits, st->kbase + kiter_rel, k.max_iters)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
   if (i > k.nx || jl > k.nyl) return;
@@ -539,13 +542,14 @@ __global__ void __launch_bounds__(PM_BX* PM_BY)
   const size_t c = pm_idx(k, jl, i);
   if (M[c]) return;
   const int P = k.pitch;
+  auto at = [&](int jj, int ii) -> double& { return p[split ? pm_sidx(k, jj, ii) : pm_idx(k, jj, ii)]; };
   double s = 0.0;
   int n = 0;
-  if (i > 1 && M[c - 1]) { s = __dadd_rn(s, p[c - 1]); ++n; }
-  if (i < k.nx && M[c + 1]) { s = __dadd_rn(s, p[c + 1]); ++n; }
-  if (j > 1 && M[c - P]) { s = __dadd_rn(s, p[c - P]); ++n; }
-  if (j < k.ny && M[c + P]) { s = __dadd_rn(s, p[c + P]); ++n; }
-  if (n > 0) p[c] = __ddiv_rn(s, double(n));
+  if (i > 1 && M[c - 1]) { s = __dadd_rn(s, at(jl, i - 1)); ++n; }
+  if (i < k.nx && M[c + 1]) { s = __dadd_rn(s, at(jl, i + 1)); ++n; }
+  if (j > 1 && M[c - P]) { s = __dadd_rn(s, at(jl - 1, i)); ++n; }
+  if (j < k.ny && M[c + P]) { s = __dadd_rn(s, at(jl + 1, i)); ++n; }
+  if (n > 0) at(jl, i) = __ddiv_rn(s, double(n));
 }
 
 // k9  residual max-norm of the current iterate -> res_bits[kiter]

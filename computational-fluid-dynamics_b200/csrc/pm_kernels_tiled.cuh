@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <string>
+#include <vector>
 
 #include "pm_common.cuh"
 #include "pm_tile_cfg.cuh"
@@ -582,13 +583,158 @@ __global__ void k_tiled_fold(unsigned long long* __restrict__ part, unsigned lon
   }
 }
 
+// ---------------------------------------------------------------------------
+// Tiles that contain solid cells (backwards-step obstacle mask, backwards_step-01.cpp:893-939).  They are few -- the rim
+// of the obstacle -- so this path is written for clarity, not speed: p stays in the shared-memory tile, every thread
+// walks its RPT x 2 cells, the mask is read from global memory.  Tiles without a single fluid cell are copied through.
+//
+// Order of one reference iteration: sweep over the fluid cells, then applyPressureGhosts -- wall ghosts, then every
+// solid cell <- mean of its fluid neighbours (:709-739) -- then the residual.  Here the solid-cell pass of iterate m is
+// done at the START of the sweep that turns iterate m into m + 1 (nothing reads a solid cell in between), so the
+// iterates stored between passes carry solid cells that lag by one such pass; pm_ppe_solve applies the last one (and
+// the wall ghosts behind solid cells, which only the stored field cares about) when the solve ends.  With that
+// placement the solid-cell pass depends on the same ring of neighbours as a colour half-sweep: solid cells of colour 0
+// read colour-1 fluid cells (final since the last half-sweep), solid cells of colour 1 read colour-0 fluid cells.
+// The lag costs one ring of the halo, though: a solid cell on the very edge of a tile arrives one ghost pass behind and
+// cannot be brought up to date (a neighbour is missing), so the stale front starts one ring further in.  A pass over a
+// masked problem therefore runs T - 1 sweeps on the geometry built for T (TiledPlan::run).  The residual of iterate m0 + t is taken in full, with the reference's tree, right after that
+// pass; its colour-1 part at the end of a pass would need solid ghosts one ring further out than are valid.
+// ---------------------------------------------------------------------------
+struct MaskedGeom {
+  int ib, jb;         // tile origin (i, jl)
+  int jI_lo, jI_hi;   // jl range this rank has data for
+  int jO_lo, jO_hi;   // jl range of the output block (clipped to this rank's rows)
+  int iO_lo, iO_hi;   // i range of the output block
+};
+template <class A, int METHOD, int T>
+__device__ __noinline__ void masked_tile(const KP& k, double* __restrict__ tile, const double* __restrict__ f, const uint8_t* __restrict__ M,
+                                         double* __restrict__ pout, unsigned long long* __restrict__ red, const MaskedGeom g, int m0, int nsw, int cls) {
+  using C = TileCfg<METHOD, T>;
+  constexpr int SW = C::SW, SH = C::SH, RPT = C::RPT;
+  static_assert(C::CS == 1 && SH * 4 * 4 <= SW * 8, "the fluid bits of the tile live in the spare row below it");
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int q = tid & 63, rr0 = (tid >> 6) * RPT;
+  auto sm = [&](int rt, int ct) -> double& { return tile[rt * SW + (ct & 1) * (SW / 2) + (ct >> 1)]; };  // split rows, see above
+  unsigned long long* redw = red + (tid >> 5) * (T + 1);
+  const int nloop = nsw > 0 ? nsw : 1;
+  if (cls == 2) {
+    // Fluid flags of the whole tile as bits, in the order of the split rows: word rt*4 + (ct&1)*2 + (ct>>6), bit (ct>>1)&31
+    // -- one ballot per row and column parity.  A flag is set for interior cells this rank has data for that are fluid.
+    uint32_t* fbits = reinterpret_cast<uint32_t*>(tile - SW);
+    auto fluid = [&](int rt, int ct) -> bool { return (fbits[rt * 4 + (ct & 1) * 2 + (ct >> 6)] >> ((ct >> 1) & 31)) & 1u; };
+    double fr[RPT][2];       // f of the thread's cells
+    unsigned own_in = 0u, own_fl = 0u;  // bit 2r+e: the cell is an interior cell with data / and fluid
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int rt = rr0 + r, jl = g.jb + rt;
+      const bool rowI = jl >= g.jI_lo && jl <= g.jI_hi;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = g.ib + 2 * q + e;
+        const bool in = rowI && i >= 1 && i <= k.nx;
+        const size_t cm = pm_idx(k, in ? jl : g.jI_lo, in ? i : 1);
+        const bool fl = in && M[cm];
+        fr[r][e] = fl ? __ldg(f + cm) : 0.0;
+        const unsigned w = __ballot_sync(0xffffffffu, fl);
+        if (lane == 0) fbits[rt * 4 + e * 2 + (q >> 5)] = w;
+        own_in |= unsigned(in) << (2 * r + e);
+        own_fl |= unsigned(fl) << (2 * r + e);
+      }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int t = 0; t < nloop; ++t) {
+      // ---- solid cells <- mean of their fluid neighbours (not before the first sweep of a solve: the reference's
+      // first sweep reads whatever the solid cells hold) ----
+      if (m0 + t > 0 && own_in != own_fl) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          const int rt = rr0 + r;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (!((own_in & ~own_fl) >> (2 * r + e) & 1u)) continue;
+            const int ct = 2 * q + e;
+            double sum = 0.0;
+            int n = 0;  // same order as backwards_step-01.cpp:716-735: west, east, south, north (is_fluid is false outside the interior)
+            if (ct >= 1 && fluid(rt, ct - 1)) { sum = __dadd_rn(sum, sm(rt, ct - 1)); ++n; }
+            if (ct <= SW - 2 && fluid(rt, ct + 1)) { sum = __dadd_rn(sum, sm(rt, ct + 1)); ++n; }
+            if (rt >= 1 && fluid(rt - 1, ct)) { sum = __dadd_rn(sum, sm(rt - 1, ct)); ++n; }
+            if (rt <= SH - 2 && fluid(rt + 1, ct)) { sum = __dadd_rn(sum, sm(rt + 1, ct)); ++n; }
+            if (n > 0) sm(rt, ct) = __ddiv_rn(sum, double(n));
+          }
+        }
+      }
+      __syncthreads();
+      // ---- residual of iterate m0 + t over the fluid cells of the output block (channel-01.cpp:676-678) ----
+      double rmax = 0.0;
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        const int rt = rr0 + r, jl = g.jb + rt;
+        if (jl < g.jO_lo || jl > g.jO_hi) continue;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ct = 2 * q + e, i = g.ib + ct;
+          if (i < g.iO_lo || i > g.iO_hi || !((own_fl >> (2 * r + e)) & 1u)) continue;
+          const double rs = res_channel<A>(k, sm(rt, ct), sm(rt, ct + 1), sm(rt, ct - 1), sm(rt + 1, ct), sm(rt - 1, ct), fr[r][e]);
+          rmax = fmax(rmax, fabs(rs));
+        }
+      }
+      {
+        const double v = warp_max_nonneg(rmax);
+        if (lane == 0) redw[t] = (unsigned long long)__double_as_longlong(v);
+      }
+      if (t >= nsw) break;  // the residual-only pass
+      __syncthreads();      // every residual has read its neighbours before the first half-sweep overwrites them
+      // ---- the two colour half-sweeps over the fluid cells; wall ghosts refreshed by the cell that owns them ----
+#pragma unroll 1
+      for (int colour = 0; colour < 2; ++colour) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          const int rt = rr0 + r, jl = g.jb + rt, j = k.j0 + jl;
+          if (rt < 1 || rt > SH - 2) continue;
+          const int e = (colour + j + g.ib) & 1;  // the cell of the pair (2q, 2q+1) with (i + j) % 2 == colour
+          const int ct = 2 * q + e, i = g.ib + ct;
+          if (ct < 1 || ct > SW - 2 || !((own_fl >> (2 * r + e)) & 1u)) continue;
+          const double nv = upd_channel<A>(k, sm(rt, ct), sm(rt, ct + 1), sm(rt, ct - 1), sm(rt + 1, ct), sm(rt - 1, ct), e ? fr[r][1] : fr[r][0]);
+          sm(rt, ct) = nv;
+          if (i == 1) sm(rt, ct - 1) = nv;      // channel-01.cpp:531-541
+          if (i == k.nx) sm(rt, ct + 1) = 0.0;
+          if (j == 1) sm(rt - 1, ct) = nv;
+          if (j == k.ny) sm(rt + 1, ct) = nv;
+        }
+        __syncthreads();
+      }
+    }
+  }
+  // ---- write the output block and the wall ghosts its cells own (a tile without fluid cells is copied through) ----
+  if (nsw > 0) {
+#pragma unroll 1
+    for (int r = 0; r < RPT; ++r) {
+      const int rt = rr0 + r, jl = g.jb + rt, j = k.j0 + jl;
+      if (jl < g.jO_lo || jl > g.jO_hi) continue;
+#pragma unroll 1
+      for (int e = 0; e < 2; ++e) {
+        const int ct = 2 * q + e, i = g.ib + ct;
+        if (i < g.iO_lo || i > g.iO_hi) continue;
+        const double v = sm(rt, ct);
+        pout[pm_sidx(k, jl, i)] = v;
+        if (i == 1) pout[pm_sidx(k, jl, 0)] = sm(rt, ct - 1);
+        if (i == k.nx) pout[pm_sidx(k, jl, k.nx + 1)] = sm(rt, ct + 1);
+        if (j == 1) pout[pm_sidx(k, jl - 1, i)] = sm(rt - 1, ct);
+        if (j == k.ny) pout[pm_sidx(k, jl + 1, i)] = sm(rt + 1, ct);
+      }
+    }
+  }
+}
+
 // Everything one CTA does for one tile once its TMA load has been issued on `bar`: masks, f loads, wait,
 // the sweeps, the write-out and the per-iterate residual atomics.
 template <class A, int FORM, int METHOD, int T, int PAR0>
 __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t* bar, uint32_t phase, unsigned long long* red,
                                              double* __restrict__ pout, const double* __restrict__ f, PpeState* __restrict__ st,
                                              unsigned long long* __restrict__ res_bits, unsigned long long* __restrict__ fold_part, int m0, int nsw, int bx, int by,
-                                             int crank, uint64_t* xbar, const int* xact, const StopWords<T>& stopw, bool check_stop) {
+                                             int crank, uint64_t* xbar, const int* xact, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ tcls,
+                                             const StopWords<T>& stopw, bool check_stop) {
   using C = TileCfg<METHOD, T>;
   constexpr int H = C::H, SW = C::SW, SH = C::SH, RPT = C::RPT, TX = C::TX, TY = C::TY, CS = C::CS;
   const int tid = threadIdx.x;
@@ -669,45 +815,57 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
   // overwrite) has landed.  Second half: before the first push into a neighbour (xchg_gate).
   if (CS > 1) cluster_arrive_relaxed();
   PM_PROF(1);  // wait for the TMA tile
-  // The tile arrived in the split-row layout: every thread takes its own cells; neighbours are read in place.
-  // No barrier: before the first half-sweep's barrier a thread only ever writes cells it owns.
-  double* tpx = tile + rr0 * SW + q;
-  double* tpy = tpx + SW / 2;
-#pragma unroll
-  for (int r = 0; r < RPT; ++r) {
-    c.p0[r] = tpx[r * SW];
-    c.p1[r] = tpy[r * SW];
+  // Obstacle mask (step case): tiles with solid cells take their own path; the classes were computed with the mask.
+  bool masked = false;
+  if constexpr (FORM == 1 && METHOD == PM_PPE_SOR_RB && CS == 1) if (tcls != nullptr) {
+    const int cls = tcls[by * int(gridDim.x) + bx];  // 0: fluid cells only, 1: no fluid cell, 2: both
+    if (cls != 0) {
+      const MaskedGeom g{ib, jb, jI_lo, jI_hi, max(1, y0), min(k.nyl, y0 + TY - 1), max(1, x0), min(k.nx, x0 + TX - 1)};
+      masked_tile<A, METHOD, T>(k, tile, f, mask, pout, red, g, m0, nsw, cls);
+      masked = true;
+    }
   }
-
-  PM_PROF(2);  // own cells
-  Xchg x;
-  x.bars = xbar;
-  x.nhs = 2 * nsw;
-  x.dn = CS > 1 && sg == 0 && xact[0];
-  x.up = CS > 1 && sg == C::NSEG - 1 && xact[1];
-  // the residual-only pass (nsw == 0) commits nothing and takes the general code path
-  if (interior && nsw > 0) run_sweeps<A, FORM, METHOD, T, true, PAR0>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red, x);
-  else run_sweeps<A, FORM, METHOD, T, false, PAR0>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red, x);
-
-  PM_PROF(3);  // the sweeps
-  // ---- write the output block (split-row layout: .x cells to the even half of the row, .y cells to the odd
-  // half, consecutive lanes to consecutive doubles), plus the wall ghosts its cells own ----
-  if (nsw > 0) {
-    const int P = k.pitch;
-    double* ox = pout + size_t(k.padr + jl0) * size_t(P) + size_t((PM_OFFC + i0 + k.psh) >> 1);  // PM_OFFC + i0 is even
-    double* oy = ox + (P >> 1);
-#pragma unroll
+  if (!masked) {
+    // The tile arrived in the split-row layout: every thread takes its own cells; neighbours are read in place.
+    // No barrier: before the first half-sweep's barrier a thread only ever writes cells it owns.
+    double* tpx = tile + rr0 * SW + q;
+    double* tpy = tpx + SW / 2;
+  #pragma unroll
     for (int r = 0; r < RPT; ++r) {
-      if (!((mO >> r) & 1u)) continue;
-      if (colO0) ox[size_t(r) * P] = c.p0[r];
-      if (colO1) oy[size_t(r) * P] = c.p1[r];
-      if (FORM == 1 && !interior) {
-        const int j = jg0 + r, jl = jl0 + r;
-        if (colO0 && i0 == 1) pout[pm_sidx(k, jl, 0)] = c.p0[r];
-        if (colO0 && i0 == k.nx) pout[pm_sidx(k, jl, k.nx + 1)] = 0.0;
-        if (colO1 && i0 + 1 == k.nx) pout[pm_sidx(k, jl, k.nx + 1)] = 0.0;
-        if (j == 1) { if (colO0) pout[pm_sidx(k, jl - 1, i0)] = c.p0[r]; if (colO1) pout[pm_sidx(k, jl - 1, i0 + 1)] = c.p1[r]; }
-        if (j == k.ny) { if (colO0) pout[pm_sidx(k, jl + 1, i0)] = c.p0[r]; if (colO1) pout[pm_sidx(k, jl + 1, i0 + 1)] = c.p1[r]; }
+      c.p0[r] = tpx[r * SW];
+      c.p1[r] = tpy[r * SW];
+    }
+
+    PM_PROF(2);  // own cells
+    Xchg x;
+    x.bars = xbar;
+    x.nhs = 2 * nsw;
+    x.dn = CS > 1 && sg == 0 && xact[0];
+    x.up = CS > 1 && sg == C::NSEG - 1 && xact[1];
+    // the residual-only pass (nsw == 0) commits nothing and takes the general code path
+    if (interior && nsw > 0) run_sweeps<A, FORM, METHOD, T, true, PAR0>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red, x);
+    else run_sweeps<A, FORM, METHOD, T, false, PAR0>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, nsw, red, x);
+
+    PM_PROF(3);  // the sweeps
+    // ---- write the output block (split-row layout: .x cells to the even half of the row, .y cells to the odd
+    // half, consecutive lanes to consecutive doubles), plus the wall ghosts its cells own ----
+    if (nsw > 0) {
+      const int P = k.pitch;
+      double* ox = pout + size_t(k.padr + jl0) * size_t(P) + size_t((PM_OFFC + i0 + k.psh) >> 1);  // PM_OFFC + i0 is even
+      double* oy = ox + (P >> 1);
+  #pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        if (!((mO >> r) & 1u)) continue;
+        if (colO0) ox[size_t(r) * P] = c.p0[r];
+        if (colO1) oy[size_t(r) * P] = c.p1[r];
+        if (FORM == 1 && !interior) {
+          const int j = jg0 + r, jl = jl0 + r;
+          if (colO0 && i0 == 1) pout[pm_sidx(k, jl, 0)] = c.p0[r];
+          if (colO0 && i0 == k.nx) pout[pm_sidx(k, jl, k.nx + 1)] = 0.0;
+          if (colO1 && i0 + 1 == k.nx) pout[pm_sidx(k, jl, k.nx + 1)] = 0.0;
+          if (j == 1) { if (colO0) pout[pm_sidx(k, jl - 1, i0)] = c.p0[r]; if (colO1) pout[pm_sidx(k, jl - 1, i0 + 1)] = c.p1[r]; }
+          if (j == k.ny) { if (colO0) pout[pm_sidx(k, jl + 1, i0)] = c.p0[r]; if (colO1) pout[pm_sidx(k, jl + 1, i0 + 1)] = c.p1[r]; }
+        }
       }
     }
   }
@@ -740,7 +898,8 @@ template <class A, int FORM, int METHOD, int T, int PAR0>
 __global__ void __launch_bounds__((TileCfg<METHOD, T>::THREADS), PM_TILE_MINBLOCKS)
     k_ppe_tiled(const __grid_constant__ KP k, const __grid_constant__ CUtensorMap tmap_in, double* __restrict__ pout,
                 const double* __restrict__ f, PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits,
-                unsigned long long* __restrict__ fold_part, int m0, int nsw, int force, int tile_row0) {
+                unsigned long long* __restrict__ fold_part, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ tcls,
+                int m0, int nsw, int force, int tile_row0) {
   using C = TileCfg<METHOD, T>;
   constexpr int CS = C::CS;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -795,7 +954,7 @@ __global__ void __launch_bounds__((TileCfg<METHOD, T>::THREADS), PM_TILE_MINBLOC
 #ifdef PM_TILE_PROFILE
   if (tid == 0) atomicAdd(&g_tile_prof[5], (unsigned long long)(clock64() - prof_k));
 #endif
-  tile_process<A, FORM, METHOD, T, PAR0>(k, tile, &mbar, 0u, red, pout, f, st, res_bits, fold_part, m0, nsw, bx, by, crank, xbar, xact, stopw, !force);
+  tile_process<A, FORM, METHOD, T, PAR0>(k, tile, &mbar, 0u, red, pout, f, st, res_bits, fold_part, m0, nsw, bx, by, crank, xbar, xact, mask, tcls, stopw, !force);
 }
 
 // Whole-plane conversion between the natural and the split-row layout (a permutation inside every row).
@@ -821,7 +980,9 @@ __global__ void k_split_rows(const __grid_constant__ KP k, const double* __restr
 // host side
 // ---------------------------------------------------------------------------
 struct TiledPlan {
-  int sweeps = 1;       // T
+  int sweeps = 1;       // T: temporal-blocking depth the tile geometry (halo) was built for
+  int run = 1;          // sweeps actually done per pass: T, or T - 1 with an obstacle mask (see masked_tile: the solid cells of the
+                        // stored iterates lag one ghost pass behind, which costs one ring of the halo)
   int halo = 2;         // H
   int tx = 0, ty = 0;   // output block
   int sh = 0, threads = 0;  // tile rows, threads per CTA
@@ -835,6 +996,8 @@ struct TiledPlan {
   const void* kernel = nullptr;
   unsigned long long* fold_part = nullptr;  // PM_FOLD_SLOTS * 16 words
   size_t fold_bytes = 0;
+  const uint8_t* mask = nullptr;        // obstacle mask plane (step case), else null
+  uint8_t* tile_class = nullptr;        // per output block: 0 fluid cells only, 1 no fluid cell, 2 both (step case), else null
 };
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -842,7 +1005,8 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static inline bool tiled_supported(const pm_config& c, const KP& k) {
-  if (c.case_id == PM_CASE_STEP) return false;  // the obstacle mask stays on the general path
+  // the obstacle mask: red-black only, independent tiles only (masked_tile does not take part in a cluster's exchange)
+  if (c.case_id == PM_CASE_STEP && (c.ppe_method != PM_PPE_SOR_RB || PM_TILE_CS != 1)) return false;
   if (c.ppe_method != PM_PPE_JACOBI && c.ppe_method != PM_PPE_SOR_RB) return false;
   if (k.pitch < 128) return false;
   return true;
@@ -882,6 +1046,8 @@ static const void* tiled_pick(int method, int T, int par0, TiledPlan* pl) {
 static inline bool tiled_create(TiledPlan* pl, const pm_config& c, const KP& k, double* p0, double* p1, int rows_alloc, std::string* err) {
   // measured at 8192^2: production red-black 13.8 ms/step at T = 4 (14.6 at 3); exact arithmetic 22.3 at T = 3 (23.6 at 4)
   int T = c.sweeps_per_pass > 0 ? c.sweeps_per_pass : (c.ppe_method == PM_PPE_SOR_RB ? (c.exact_arith ? 3 : 4) : 2);
+  const bool masked = c.case_id == PM_CASE_STEP;
+  if (masked) T = c.sweeps_per_pass > 0 ? std::min(4, c.sweeps_per_pass + 1) : 4;  // geometry one sweep deeper than what a pass runs
   const bool cav = c.case_id == PM_CASE_CAVITY;
   const void* kern = nullptr;
   const int par0 = k.j0 & 1;
@@ -889,6 +1055,7 @@ static inline bool tiled_create(TiledPlan* pl, const pm_config& c, const KP& k, 
   else kern = cav ? tiled_pick<Fast, 0>(c.ppe_method, T, par0, pl) : tiled_pick<Fast, 1>(c.ppe_method, T, par0, pl);
   if (!kern) { *err = "sweeps_per_pass " + std::to_string(T) + " not built for this method (red-black: 1,2,3,4; jacobi: 1,2,4)"; return false; }
   pl->kernel = kern;
+  pl->run = masked ? pl->sweeps - 1 : pl->sweeps;
   pl->tiles_x = (k.nx + pl->tx - 1) / pl->tx;
   pl->tiles_y = (k.nyl + pl->ty - 1) / pl->ty;
   pl->p[0] = p0; pl->p[1] = p1;
@@ -916,7 +1083,36 @@ static inline bool tiled_create(TiledPlan* pl, const pm_config& c, const KP& k, 
 }
 static inline void tiled_destroy(TiledPlan* pl) {
   if (pl->fold_part) cudaFree(pl->fold_part);
+  if (pl->tile_class) cudaFree(pl->tile_class);
   pl->fold_part = nullptr;
+  pl->tile_class = nullptr;
+}
+// Classes of the output blocks for an obstacle mask (global array, (ny+2) x (nx+2) bytes): looked at over the whole
+// tile around each block, ring included, clipped to the interior cells this rank has data for.
+static inline bool tiled_classify(TiledPlan* pl, const KP& k, const uint8_t* global_mask, cudaStream_t stream, std::string* err) {
+  const int ntiles = pl->tiles_x * pl->tiles_y;
+  std::vector<uint8_t> cls(size_t(ntiles), 0);
+  const int cols = k.nx + 2;
+  for (int by = 0; by < pl->tiles_y; ++by)
+    for (int bx = 0; bx < pl->tiles_x; ++bx) {
+      const int ib = 1 + bx * pl->tx - pl->halo, jb = 1 + by * pl->ty - pl->halo;
+      const int jl_lo = std::max(std::max(1 - k.j0, 1 - pl->halo), jb), jl_hi = std::min(std::min(k.ny - k.j0, k.nyl + pl->halo), jb + pl->sh - 1);
+      const int i_lo = std::max(1, ib), i_hi = std::min(k.nx, ib + 128 - 1);
+      bool any_fluid = false, any_solid = false;
+      for (int jl = jl_lo; jl <= jl_hi && !(any_fluid && any_solid); ++jl) {
+        const uint8_t* row = global_mask + size_t(k.j0 + jl) * cols;
+        for (int i = i_lo; i <= i_hi; ++i) {
+          if (row[i]) any_fluid = true; else any_solid = true;
+        }
+      }
+      cls[size_t(by) * pl->tiles_x + bx] = !any_solid ? 0 : (!any_fluid ? 1 : 2);
+    }
+  cudaError_t e = cudaSuccess;
+  if (!pl->tile_class) e = cudaMalloc(&pl->tile_class, size_t(ntiles));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pl->tile_class, cls.data(), size_t(ntiles), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) { *err = std::string("tile classes: ") + cudaGetErrorString(e); return false; }
+  return true;
 }
 // Before the first pass of a solve (stream order): empty slots.
 static inline cudaError_t tiled_begin_solve(const TiledPlan* pl, cudaStream_t stream) {
@@ -928,7 +1124,7 @@ static inline cudaError_t tiled_launch(const TiledPlan* pl, const KP& k, int in,
                                        int m0, int nsw, int force, int tile_row0, int tile_rows, cudaStream_t stream) {
   double* pout = pl->p[in ^ 1];
   void* args[] = {(void*)&k, (void*)&pl->map[in], (void*)&pout, (void*)&f, (void*)&st, (void*)&res, (void*)&pl->fold_part,
-                  (void*)&m0, (void*)&nsw, (void*)&force, (void*)&tile_row0};
+                  (void*)&pl->mask, (void*)&pl->tile_class, (void*)&m0, (void*)&nsw, (void*)&force, (void*)&tile_row0};
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3(pl->tiles_x, tile_rows * pl->cs);
   lc.blockDim = dim3(pl->threads);

@@ -62,6 +62,10 @@ def main():
         (pm.CASE_STEP, 256, 16, pm.PPE_JACOBI, 1, pm.PATH_SIMPLE, 0, 30, 3),
         (pm.CASE_STEP, 320, 45, pm.PPE_SOR_RB, 0, pm.PATH_AUTO, 0, 25, 2),
         (pm.CASE_STEP, 256, 16, pm.PPE_SOR_RB, 1, pm.PATH_SIMPLE, 0, 10000, 2),
+        # obstacle mask on the tiled path: fluid-only, solid-only and mixed tiles, several tile rows per slab, 8-row halos
+        (pm.CASE_STEP, 1100, 300, pm.PPE_SOR_RB, 1, pm.PATH_TILED, 4, 22, 2),
+        (pm.CASE_STEP, 1100, 301, pm.PPE_SOR_RB, 1, pm.PATH_TILED, 3, 20, 2),
+        (pm.CASE_STEP, 900, 260, pm.PPE_SOR_RB, 0, pm.PATH_AUTO, 0, 25, 2),
     ]
     failures = 0
     for (case, nx, nyr, method, exact, path, T, K, steps) in cases:

@@ -260,6 +260,8 @@ TILED_CASES = [
     (0, 48, 48, RB, 1), (0, 48, 48, RB, 2), (0, 250, 131, RB, 2), (0, 250, 131, RB, 3), (0, 117, 61, RB, 3), (0, 250, 131, RB, 4), (0, 117, 61, RB, 4),
     (1, 93, 31, RB, 1), (1, 93, 31, RB, 2), (1, 300, 70, RB, 2), (1, 300, 70, RB, 3), (1, 121, 77, RB, 3), (1, 300, 70, RB, 4),
     (0, 48, 48, JAC, 1), (0, 250, 131, JAC, 2), (0, 250, 131, JAC, 4), (1, 93, 31, JAC, 1), (1, 300, 70, JAC, 2), (1, 300, 70, JAC, 4),
+    # obstacle mask (backwards step): tiles with fluid cells only, with solid cells only, and with both
+    (2, 64, 16, RB, 1), (2, 256, 32, RB, 2), (2, 300, 70, RB, 3), (2, 300, 70, RB, 4), (2, 250, 131, RB, 4), (2, 117, 61, RB, 3), (2, 640, 200, RB, 4),
 ]
 
 
@@ -279,7 +281,7 @@ def test_tiled_ppe_bit_exact(pm, orc, case_id, nx, ny, method, T, K):
 
 
 @pytest.mark.parametrize("case_id,nx,ny,method,T", [(0, 400, 300, RB, 3), (0, 400, 300, RB, 2), (0, 400, 300, RB, 4), (1, 384, 200, RB, 3), (1, 384, 200, RB, 4), (0, 400, 300, JAC, 2),
-                                                   (1, 384, 200, JAC, 4)])
+                                                   (1, 384, 200, JAC, 4), (2, 640, 200, RB, 4), (2, 384, 200, RB, 3)])
 def test_tiled_production_arithmetic_close_to_oracle(pm, orc, case_id, nx, ny, method, T):
     """Production arithmetic on the tiled path, grids with interior tiles (the residual-form relaxation with
     summed neighbours): iterate within 1e-12 of the oracle's relative to the field's scale, residual norm to
@@ -295,7 +297,8 @@ def test_tiled_production_arithmetic_close_to_oracle(pm, orc, case_id, nx, ny, m
     assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(b).max()), f"p off by {np.abs(a - b).max():.3e} vs scale {np.abs(b).max():.3e}"
 
 
-@pytest.mark.parametrize("case_id,nx,ny,T,steps", [(0, 40, 40, 2, 4), (0, 40, 40, 3, 4), (0, 40, 40, 4, 4), (1, 93, 31, 2, 2), (1, 93, 31, 3, 2), (1, 93, 31, 4, 2)])
+@pytest.mark.parametrize("case_id,nx,ny,T,steps", [(0, 40, 40, 2, 4), (0, 40, 40, 3, 4), (0, 40, 40, 4, 4), (1, 93, 31, 2, 2), (1, 93, 31, 3, 2), (1, 93, 31, 4, 2),
+                                                   (2, 64, 16, 2, 2), (2, 64, 16, 4, 2), (2, 96, 24, 3, 2)])
 def test_tiled_stopping_rule_bit_exact(pm, orc, case_id, nx, ny, T, steps):
     """Run to the reference tolerance through the tiled path: the device-side loop test plus the
     partial replay pass must land on exactly the iterate the oracle stops at."""
@@ -325,6 +328,68 @@ def test_cluster_build_bit_exact():
                           "tiled_ppe_bit_exact or tiled_production or tiled_stopping or ragged or auto_path"],
                          env=env, capture_output=True, text=True, timeout=1200)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+
+
+def blob_mask(nx, ny, seed):
+    """An irregular obstacle field: rectangles, single solid cells, one-cell gaps, solids against every wall."""
+    rng = np.random.default_rng(seed)
+    m = np.zeros((ny + 2, nx + 2), dtype=np.uint8)
+    m[1:ny + 1, 1:nx + 1] = 1
+    for _ in range(14):
+        h, w = int(rng.integers(1, max(2, ny // 4))), int(rng.integers(1, max(2, nx // 5)))
+        j, i = int(rng.integers(1, ny - h + 2)), int(rng.integers(1, nx - w + 2))
+        m[j:j + h, i:i + w] = 0
+    for _ in range(40):
+        m[int(rng.integers(1, ny + 1)), int(rng.integers(1, nx + 1))] = 0
+    m[1:ny + 1, 1][::3] = 0  # solid cells on the inlet wall, the outlet wall and both plates
+    m[ny, 1:nx + 1][::5] = 0
+    m[1, 1:nx + 1][::7] = 0
+    m[1:ny + 1, nx][::4] = 0
+    return m
+
+
+@pytest.mark.parametrize("nx,ny,T,seed", [(300, 131, 4, 1), (259, 97, 3, 2), (130, 60, 2, 3), (640, 200, 4, 4)])
+@pytest.mark.parametrize("path", [1, 2])
+def test_arbitrary_obstacle_mask_bit_exact(pm, orc, nx, ny, T, seed, path):
+    """pm_upload_mask with an irregular obstacle field (the reference only ever builds one rectangle, but its loops are
+    written for any is_fluid): whole steps through the general and the tiled path against the oracle, 0 ulp."""
+    cfg = make_cfg(pm, 2, nx, ny, RB, 1, 21, path=path)
+    cfg.sweeps_per_pass = T if path == 2 else 0
+    m = blob_mask(nx, ny, seed)
+    S, O = pm.Solver(cfg), orc.Oracle(cfg)
+    S.upload_mask(m)
+    O.mask()[:] = m
+    S.fill_random(9, 2.0 ** -3); O.fill_random(9, 2.0 ** -3)
+    S.apply_bc(0); O.apply_bc(0)
+    for n in range(2):
+        rs, ro = S.step(1), O.step(1)
+        assert (rs.iterations, rs.residual) == (ro.iterations, ro.residual), f"step {n}"
+    assert_fields_equal(S, O, range(6), "obstacle field")
+
+
+@pytest.mark.parametrize("exact", [1, 0])
+def test_large_step_grid_tiled_equals_general_path(pm, exact):
+    """The obstacle mask at a size with thousands of tiles (2048 x 512: fluid-only, solid-only and mixed tiles, 8 mixed
+    tile rows): tiled path == general path, bit for bit with exact arithmetic, 1e-12 with production arithmetic."""
+    out = []
+    for path, T in ((1, 0), (2, 4), (2, 3)):
+        cfg = make_cfg(pm, 2, 2048, 512, RB, exact, 13, path=path)
+        cfg.sweeps_per_pass = T
+        S = pm.Solver(cfg)
+        S.fill_random(5, 2.0 ** -6)
+        S.apply_bc(0)
+        r = S.step(2)
+        assert r.iterations == 13 and r.hit_cap == 1
+        out.append((r.residual, S.download(2), S.download(0), S.download(1)))
+        S.close()
+    for o in out[1:]:
+        if exact:
+            assert o[0] == out[0][0]
+            assert all(bits_equal(a, b) for a, b in zip(o[1:], out[0][1:]))
+        else:
+            assert abs(o[0] - out[0][0]) <= 1e-9 * out[0][0]
+            for a, b in zip(o[1:], out[0][1:]):
+                assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(b).max())
 
 
 @pytest.mark.parametrize("exact", [1, 0])
@@ -519,8 +584,6 @@ def test_auto_path_mid_size_bit_exact(pm, orc, case_id, nx, ny, method):
 def test_ragged_and_tiny_grids_bit_exact(pm, orc, case_id, nx, ny, path):
     """Edge sizes: the smallest legal grids, odd extents (column pairs straddling the east wall), grids of exactly
     one output tile and one cell more — through the general, persistent and tiled paths."""
-    if path == 2 and case_id == 2:
-        pytest.skip("the masked step case has no tiled path")
     cfg = make_cfg(pm, case_id, nx, ny, RB, 1, 12, path=path)
     if case_id == 2:
         cfg.step_i_location, cfg.inlet_j_max = 2, 2
