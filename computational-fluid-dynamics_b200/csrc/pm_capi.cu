@@ -627,13 +627,15 @@ extern "C" int pm_predict(pm_solver* s) {
   const KP& k = s->kp;
   PMTRY(exchange_halo1(s, s->pl[PL_U]));
   PMTRY(exchange_halo1(s, s->pl[PL_V]));
-  if (!k.has_mask) {  // unmasked: two cells per thread, 128-bit rows
-    if (s->cfg.exact_arith) k_predict_rows<Exact><<<rows_grid(k), rows_block(), 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->pl[PL_US], s->pl[PL_VS]);
-    else k_predict_rows<Fast><<<rows_grid(k), rows_block(), 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->pl[PL_US], s->pl[PL_VS]);
-  } else if (s->cfg.exact_arith)
-    k_predict<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->mask, s->pl[PL_US], s->pl[PL_VS]);
-  else
-    k_predict<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->mask, s->pl[PL_US], s->pl[PL_VS]);
+  // two cells per thread, 128-bit rows; the obstacle mask rides along as byte pairs
+  const dim3 g = rows_grid(k), b = rows_block();
+  if (k.has_mask) {
+    if (s->cfg.exact_arith) k_predict_rows<Exact, true><<<g, b, 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->mask, s->pl[PL_US], s->pl[PL_VS]);
+    else k_predict_rows<Fast, true><<<g, b, 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->mask, s->pl[PL_US], s->pl[PL_VS]);
+  } else {
+    if (s->cfg.exact_arith) k_predict_rows<Exact, false><<<g, b, 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->mask, s->pl[PL_US], s->pl[PL_VS]);
+    else k_predict_rows<Fast, false><<<g, b, 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->mask, s->pl[PL_US], s->pl[PL_VS]);
+  }
   CKL(s);
   return PM_OK;
 }
@@ -647,17 +649,16 @@ extern "C" int pm_source(pm_solver* s) {
   PMTRY(exchange_halo1(s, s->pl[PL_VS]));  // f[1][i] reads v*[0][i] of the slab below
   CK(cudaMemsetAsync(&s->d_state->maxf_bits, 0, 2 * sizeof(unsigned long long), s->stream));
   double* partial = (!cav && !exact) ? s->d_partial : nullptr;
-  int n_partial = s->n_partial;  // blocks that wrote a partial sum
-  if (!k.has_mask) {
-    const dim3 g = rows_grid(k);
-    n_partial = int(g.x * g.y);
-    if (n_partial > s->cap_partial) return fail(s, PM_ERR_RUNTIME, "partial-sum buffer too small: %d blocks, %d slots", n_partial, s->cap_partial);
-    if (exact) k_source_rows<Exact><<<g, rows_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->pl[PL_F], s->d_state, partial);
-    else k_source_rows<Fast><<<g, rows_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->pl[PL_F], s->d_state, partial);
-  } else if (exact)
-    k_source<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->mask, s->pl[PL_F], s->d_state, partial);
-  else
-    k_source<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->mask, s->pl[PL_F], s->d_state, partial);
+  const dim3 g = rows_grid(k), b = rows_block();
+  const int n_partial = int(g.x * g.y);  // blocks that write a partial sum
+  if (n_partial > s->cap_partial) return fail(s, PM_ERR_RUNTIME, "partial-sum buffer too small: %d blocks, %d slots", n_partial, s->cap_partial);
+  if (k.has_mask) {
+    if (exact) k_source_rows<Exact, true><<<g, b, 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->mask, s->pl[PL_F], s->d_state, partial);
+    else k_source_rows<Fast, true><<<g, b, 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->mask, s->pl[PL_F], s->d_state, partial);
+  } else {
+    if (exact) k_source_rows<Exact, false><<<g, b, 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->mask, s->pl[PL_F], s->d_state, partial);
+    else k_source_rows<Fast, false><<<g, b, 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->mask, s->pl[PL_F], s->d_state, partial);
+  }
   CKL(s);
   if (cav) {
     // the tolerance rule reads max|f| of this very pass (cavity-01.cpp:628-632)
@@ -678,7 +679,11 @@ extern "C" int pm_source(pm_solver* s) {
       static_assert(sizeof(double) == sizeof(unsigned long long), "");
       if (!pm_nccl_bcast_words(&s->nccl, s->stream, reinterpret_cast<unsigned long long*>(&s->d_state->mean), 1, last, &e))
         return fail(s, PM_ERR_NCCL, "%s", e.c_str());
-      k_sub_mean<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+      {
+        const dim3 gm = rows_grid(k), bm = rows_block();
+        if (k.has_mask) k_sub_mean_rows<Exact, true><<<gm, bm, 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+        else k_sub_mean_rows<Exact, false><<<gm, bm, 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+      }
       CKL(s);
     } else {
       k_sum_partials<<<1, 1024, 0, s->stream>>>(s->d_partial, n_partial, s->d_state);  // local sum -> ke_sum scratch
@@ -686,7 +691,11 @@ extern "C" int pm_source(pm_solver* s) {
       if (!pm_nccl_allreduce_sum_f64(&s->nccl, s->stream, &s->d_state->ke_sum, 1, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
       k_mean_from_sum<<<1, 1, 0, s->stream>>>(k.fluid_count_global, s->d_state);
       CKL(s);
-      k_sub_mean<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+      {
+        const dim3 gm = rows_grid(k), bm = rows_block();
+        if (k.has_mask) k_sub_mean_rows<Fast, true><<<gm, bm, 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+        else k_sub_mean_rows<Fast, false><<<gm, bm, 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+      }
       CKL(s);
     }
     if (!pm_nccl_allreduce_max_u64(&s->nccl, s->stream, &s->d_state->maxf2_bits, 1, &e)) return fail(s, PM_ERR_NCCL, "%s", e.c_str());
@@ -696,11 +705,19 @@ extern "C" int pm_source(pm_solver* s) {
   if (exact) {
     k_mean_serial<<<1, 32, 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state, 0);
     CKL(s);
-    k_sub_mean<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+    {
+        const dim3 gm = rows_grid(k), bm = rows_block();
+        if (k.has_mask) k_sub_mean_rows<Exact, true><<<gm, bm, 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+        else k_sub_mean_rows<Exact, false><<<gm, bm, 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+      }
   } else {
     k_mean_from_partials<<<1, 1024, 0, s->stream>>>(s->d_partial, n_partial, k.fluid_count_global, s->d_state);
     CKL(s);
-    k_sub_mean<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+    {
+        const dim3 gm = rows_grid(k), bm = rows_block();
+        if (k.has_mask) k_sub_mean_rows<Fast, true><<<gm, bm, 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+        else k_sub_mean_rows<Fast, false><<<gm, bm, 0, s->stream>>>(k, s->pl[PL_F], s->mask, s->d_state);
+      }
   }
   CKL(s);
   s->f_max_valid = true;
@@ -734,13 +751,16 @@ extern "C" int pm_correct(pm_solver* s) {
   const int psplit = s->use_tiled && s->p_split && !s->p_nat;
   const double* p = psplit ? s->tp[s->tp_cur] : s->pl[s->p_cur];
   PMTRY(exchange_halo1(s, const_cast<double*>(p)));
-  if (!k.has_mask) {
-    if (s->cfg.exact_arith) k_correct_rows<Exact><<<rows_grid(k), rows_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], p, s->pl[PL_U], s->pl[PL_V], psplit);
-    else k_correct_rows<Fast><<<rows_grid(k), rows_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], p, s->pl[PL_U], s->pl[PL_V], psplit);
-  } else if (s->cfg.exact_arith)
-    k_correct<Exact><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], p, s->mask, s->pl[PL_U], s->pl[PL_V], psplit);
-  else
-    k_correct<Fast><<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], p, s->mask, s->pl[PL_U], s->pl[PL_V], psplit);
+  {
+    const dim3 g = rows_grid(k), b = rows_block();
+    if (k.has_mask) {
+      if (s->cfg.exact_arith) k_correct_rows<Exact, true><<<g, b, 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], p, s->mask, s->pl[PL_U], s->pl[PL_V], psplit);
+      else k_correct_rows<Fast, true><<<g, b, 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], p, s->mask, s->pl[PL_U], s->pl[PL_V], psplit);
+    } else {
+      if (s->cfg.exact_arith) k_correct_rows<Exact, false><<<g, b, 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], p, s->mask, s->pl[PL_U], s->pl[PL_V], psplit);
+      else k_correct_rows<Fast, false><<<g, b, 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], p, s->mask, s->pl[PL_U], s->pl[PL_V], psplit);
+    }
+  }
   CKL(s);
   return PM_OK;
 }

@@ -125,30 +125,8 @@ __device__ __forceinline__ double pred_v(const KP& k, double vc, double ve_, dou
   return A::add(vc, A::mul(k.dt, A::sub(A::sub(diff, cy), cx)));
 }
 
-// General kernel (any case, obstacle mask): one thread per cell.
-template <class A>
-__global__ void __launch_bounds__(PM_BX* PM_BY)
-    k_predict(const __grid_constant__ KP k, const double* __restrict__ u, const double* __restrict__ v,
-              const uint8_t* __restrict__ M, double* __restrict__ us, double* __restrict__ vs) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  if (i > k.nx || jl > k.nyl) return;
-  const int j = k.j0 + jl;
-  const size_t c = pm_idx(k, jl, i);
-  const int P = k.pitch;
-  const double uc = u[c], uw = u[c - 1], vc = v[c], vS = v[c - P];
-  const bool do_u = i <= k.nx - 1, do_v = j <= k.ny - 1;
-  const double ue_ = do_u ? u[c + 1] : 0.0;  // u has nx+1 columns: i+1 exists only for i <= nx-1
-  const double uN = u[c + P], uS = u[c - P];
-  const double ve_ = v[c + 1], vw_ = v[c - 1];
-  bool fl_c = true, fl_e = true, fl_n = true;
-  if (k.has_mask) { fl_c = M[c]; fl_e = M[c + 1]; fl_n = M[c + P]; }
-  if (do_u) us[c] = (fl_c || fl_e) ? pred_u<A>(k, uc, uw, ue_, uN, uS, vc, ve_, vS, v[c - P + 1]) : 0.0;
-  if (do_v) vs[c] = (fl_c || fl_n) ? pred_v<A>(k, vc, ve_, vw_, v[c + P], vS, uc, uN, uw, u[c + P - 1]) : 0.0;
-}
-
 // ---------------------------------------------------------------------------
-// Row kernels for the unmasked cases (cavity, channel): two cells per thread -- columns i, i+1 with i odd, so the
+// Row kernels (every case): two cells per thread -- columns i, i+1 with i odd, so the
 // pair starts at an even storage column -- every field moved with 128-bit loads and stores, the same per-cell
 // expression trees as the general kernels.  Block 128 x 2 threads = 256 columns x 2 rows.
 // ---------------------------------------------------------------------------
@@ -157,10 +135,11 @@ __global__ void __launch_bounds__(PM_BX* PM_BY)
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 
-template <class A>
+// MASK: the obstacle mask of the step case (backwards_step-01.cpp:755-761,790-796: a face between two solid cells is 0).
+template <class A, bool MASK>
 __global__ void __launch_bounds__(PM_RX* PM_RY)
-    k_predict_rows(const __grid_constant__ KP k, const double* __restrict__ u, const double* __restrict__ v, double* __restrict__ us,
-                   double* __restrict__ vs) {
+    k_predict_rows(const __grid_constant__ KP k, const double* __restrict__ u, const double* __restrict__ v, const uint8_t* __restrict__ M,
+                   double* __restrict__ us, double* __restrict__ vs) {
   const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x) + 1;
   const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
   if (i > k.nx || jl > k.nyl) return;
@@ -173,13 +152,20 @@ __global__ void __launch_bounds__(PM_RX* PM_RY)
   const double vW = v[c - 1], vE2 = v[c + 2], vSE2 = v[c - P + 2];
   const bool a_u = i <= k.nx - 1, b_u = i + 1 <= k.nx - 1;  // u* columns 1..nx-1
   const bool a_v = j <= k.ny - 1, b_v = a_v && i + 1 <= k.nx;  // v* rows 1..ny-1, columns 1..nx
-  const double ua = pred_u<A>(k, U.x, uW, U.y, UN.x, US.x, V.x, V.y, VS.x, VS.y);
-  const double ub = pred_u<A>(k, U.y, U.x, uE2, UN.y, US.y, V.y, vE2, VS.y, vSE2);
+  bool ua_on = true, ub_on = true, va_on = true, vb_on = true;
+  if (MASK) {  // PM_OFFC + i is even: the pair's mask bytes sit on a 2-byte boundary
+    const uchar2 mc = *reinterpret_cast<const uchar2*>(M + c), mn = *reinterpret_cast<const uchar2*>(M + c + P);
+    const uint8_t me2 = M[c + 2];
+    ua_on = mc.x || mc.y; ub_on = mc.y || me2;
+    va_on = mc.x || mn.x; vb_on = mc.y || mn.y;
+  }
+  const double ua = ua_on ? pred_u<A>(k, U.x, uW, U.y, UN.x, US.x, V.x, V.y, VS.x, VS.y) : 0.0;
+  const double ub = ub_on ? pred_u<A>(k, U.y, U.x, uE2, UN.y, US.y, V.y, vE2, VS.y, vSE2) : 0.0;
   if (a_u && b_u) st2(us + c, ua, ub);
   else if (a_u) us[c] = ua;
   if (a_v) {
-    const double va = pred_v<A>(k, V.x, V.y, vW, VN.x, VS.x, U.x, UN.x, uW, uNW);
-    const double vb = pred_v<A>(k, V.y, vE2, V.x, VN.y, VS.y, U.y, UN.y, U.x, UN.x);
+    const double va = va_on ? pred_v<A>(k, V.x, V.y, vW, VN.x, VS.x, U.x, UN.x, uW, uNW) : 0.0;
+    const double vb = vb_on ? pred_v<A>(k, V.y, vE2, V.x, VN.y, VS.y, U.y, UN.y, U.x, UN.x) : 0.0;
     if (b_v) st2(vs + c, va, vb);
     else vs[c] = va;
   }
@@ -189,38 +175,11 @@ __global__ void __launch_bounds__(PM_RX* PM_RY)
 // k4  divergence source + max|f|  (cavity-01.cpp:622-630; channel-01.cpp:613-619;
 //     backwards_step-01.cpp:830-841).  Also per-block partial sums for the mean.
 // ---------------------------------------------------------------------------
-template <class A>
-__global__ void __launch_bounds__(PM_BX* PM_BY)
-    k_source(const __grid_constant__ KP k, const double* __restrict__ us, const double* __restrict__ vs,
-             const uint8_t* __restrict__ M, double* __restrict__ f, PpeState* __restrict__ st,
-             double* __restrict__ partial /* one per block, or null */) {
-  __shared__ double sh[32];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  double a = 0.0, val = 0.0;
-  if (i <= k.nx && jl <= k.nyl) {
-    const size_t c = pm_idx(k, jl, i);
-    if (!k.has_mask || M[c]) {
-      const double du = A::mul(A::sub(us[c], us[c - 1]), k.idx);
-      const double dv = A::mul(A::sub(vs[c], vs[c - k.pitch]), k.idy);
-      val = A::mul(k.src_coef, A::add(du, dv));
-      a = fabs(val);
-    }
-    f[c] = val;
-  }
-  const double m = block_max(a, sh);
-  if (threadIdx.x == 0 && threadIdx.y == 0) atomic_max_nonneg(&st->maxf_bits, m);
-  if (partial) {
-    const double s = block_sum(val, sh);
-    if (threadIdx.x == 0 && threadIdx.y == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
-  }
-}
-
-// Row version for the unmasked cases (see k_predict_rows).
-template <class A>
+// Row version (see k_predict_rows).  MASK: solid cells get f = 0 and stay out of the maximum and the sum.
+template <class A, bool MASK>
 __global__ void __launch_bounds__(PM_RX* PM_RY)
-    k_source_rows(const __grid_constant__ KP k, const double* __restrict__ us, const double* __restrict__ vs, double* __restrict__ f,
-                  PpeState* __restrict__ st, double* __restrict__ partial /* one per block, or null */) {
+    k_source_rows(const __grid_constant__ KP k, const double* __restrict__ us, const double* __restrict__ vs, const uint8_t* __restrict__ M,
+                  double* __restrict__ f, PpeState* __restrict__ st, double* __restrict__ partial /* one per block, or null */) {
   __shared__ double sh[32];
   const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x) + 1;
   const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
@@ -229,9 +188,14 @@ __global__ void __launch_bounds__(PM_RX* PM_RY)
     const size_t c = pm_idx(k, jl, i);
     const double2 U = ld2(us + c), V = ld2(vs + c), VS = ld2(vs + c - k.pitch);
     const double uW = us[c - 1];
-    const double fa = A::mul(k.src_coef, A::add(A::mul(A::sub(U.x, uW), k.idx), A::mul(A::sub(V.x, VS.x), k.idy)));
+    bool fa_on = true, fb_on = true;
+    if (MASK) {
+      const uchar2 mc = *reinterpret_cast<const uchar2*>(M + c);
+      fa_on = mc.x; fb_on = mc.y;
+    }
+    const double fa = fa_on ? A::mul(k.src_coef, A::add(A::mul(A::sub(U.x, uW), k.idx), A::mul(A::sub(V.x, VS.x), k.idy))) : 0.0;
     if (i + 1 <= k.nx) {
-      const double fb = A::mul(k.src_coef, A::add(A::mul(A::sub(U.y, U.x), k.idx), A::mul(A::sub(V.y, VS.y), k.idy)));
+      const double fb = fb_on ? A::mul(k.src_coef, A::add(A::mul(A::sub(U.y, U.x), k.idx), A::mul(A::sub(V.y, VS.y), k.idy))) : 0.0;
       st2(f + c, fa, fb);
       a = fmax(fabs(fa), fabs(fb));
       sum = fa + fb;
@@ -247,6 +211,37 @@ __global__ void __launch_bounds__(PM_RX* PM_RY)
     const double s = block_sum(sum, sh);
     if (threadIdx.x == 0 && threadIdx.y == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
   }
+}
+
+// f -= mean on (fluid) cells when max|f| > 0, and max|f| of the result (channel-01.cpp:621-628, :643-646): row version.
+template <class A, bool MASK>
+__global__ void __launch_bounds__(PM_RX* PM_RY)
+    k_sub_mean_rows(const __grid_constant__ KP k, double* __restrict__ f, const uint8_t* __restrict__ M, PpeState* __restrict__ st) {
+  __shared__ double sh[32];
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x) + 1;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const bool apply = st->maxf_bits != 0ull;
+  const double mean = st->mean;
+  double a = 0.0;
+  if (i <= k.nx && jl <= k.nyl) {
+    const size_t c = pm_idx(k, jl, i);
+    const bool two = i + 1 <= k.nx;
+    bool xa = true, xb = two;
+    if (MASK) {
+      const uchar2 mc = *reinterpret_cast<const uchar2*>(M + c);
+      xa = mc.x; xb = two && mc.y;
+    }
+    double2 F = two ? ld2(f + c) : make_double2(f[c], 0.0);
+    if (apply) {
+      if (xa) F.x = A::sub(F.x, mean);
+      if (xb) F.y = A::sub(F.y, mean);
+      if (two) st2(f + c, F.x, F.y);
+      else f[c] = F.x;
+    }
+    a = fmax(xa ? fabs(F.x) : 0.0, xb ? fabs(F.y) : 0.0);
+  }
+  const double m = block_max(a, sh);
+  if (threadIdx.x == 0 && threadIdx.y == 0) atomic_max_nonneg(&st->maxf2_bits, m);
 }
 
 // Predictor + source in one pass for the cavity, where nothing happens between the two (cavity-01.cpp:388-389 and
@@ -379,29 +374,6 @@ __global__ void k_mean_serial(const __grid_constant__ KP k, const double* __rest
     st->chain[0] = (unsigned long long)__double_as_longlong(s);
     st->chain[1] = (unsigned long long)cnt;
   }
-}
-// k5/k6: f -= mean on (fluid) cells when max|f| > 0, and max|f| of the result
-// (channel-01.cpp:621-628, :643-646).
-template <class A>
-__global__ void __launch_bounds__(PM_BX* PM_BY)
-    k_sub_mean(const __grid_constant__ KP k, double* __restrict__ f, const uint8_t* __restrict__ M,
-               PpeState* __restrict__ st) {
-  __shared__ double sh[32];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  const bool apply = st->maxf_bits != 0ull;
-  const double mean = st->mean;
-  double a = 0.0;
-  if (i <= k.nx && jl <= k.nyl) {
-    const size_t c = pm_idx(k, jl, i);
-    if (!k.has_mask || M[c]) {
-      double x = f[c];
-      if (apply) { x = A::sub(x, mean); f[c] = x; }
-      a = fabs(x);
-    }
-  }
-  const double m = block_max(a, sh);
-  if (threadIdx.x == 0 && threadIdx.y == 0) atomic_max_nonneg(&st->maxf2_bits, m);
 }
 // max|f| only (cavity, or when pm_ppe_solve is called on an uploaded f).
 __global__ void __launch_bounds__(PM_BX* PM_BY)
@@ -584,38 +556,13 @@ __global__ void __launch_bounds__(PM_BX* PM_BY)
 // k10  velocity correction (cavity-01.cpp:695-711; channel-01.cpp:693-702;
 //      backwards_step-01.cpp:944-976)
 // ---------------------------------------------------------------------------
-template <class A>
-__global__ void __launch_bounds__(PM_BX* PM_BY)
-    k_correct(const __grid_constant__ KP k, const double* __restrict__ us, const double* __restrict__ vs,
-              const double* __restrict__ p, const uint8_t* __restrict__ M, double* __restrict__ u,
-              double* __restrict__ v, int psplit) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  if (i > k.nx || jl > k.nyl) return;
-  const int j = k.j0 + jl;
-  const size_t c = pm_idx(k, jl, i);
-  // psplit: p is the final buffer of the tiled solve, still in its split-row layout
-  const size_t pc_i = psplit ? pm_sidx(k, jl, i) : c, pe_i = psplit ? pm_sidx(k, jl, i + 1) : c + 1,
-               pn_i = psplit ? pm_sidx(k, jl + 1, i) : c + k.pitch;
-  const double pc = p[pc_i];
-  bool fl_c = true, fl_e = true, fl_n = true;
-  if (k.has_mask) { fl_c = M[c]; fl_e = M[c + 1]; fl_n = M[c + k.pitch]; }
-  if (i <= k.nx - 1) {
-    const bool valid = (i == k.nx - 1) || fl_c || fl_e;
-    u[c] = valid ? A::sub(us[c], A::mul(k.cu, A::sub(p[pe_i], pc))) : 0.0;
-  }
-  if (j <= k.ny - 1) {
-    const bool valid = (j == k.ny - 1) || fl_c || fl_n;
-    v[c] = valid ? A::sub(vs[c], A::mul(k.cv, A::sub(p[pn_i], pc))) : 0.0;
-  }
-}
-
-// Row version for the unmasked cases (see k_predict_rows).  psplit: p is the final buffer of the tiled solve in
-// its split-row layout, where the pair (i, i+1) is one double in each half of the row.
-template <class A>
+// Row version (see k_predict_rows).  psplit: p is the final buffer of the tiled solve in its split-row layout, where the
+// pair (i, i+1) is one double in each half of the row.  MASK: faces between two solid cells are 0, except the last u
+// column and the last v row, which the reference always corrects (backwards_step-01.cpp:950-975).
+template <class A, bool MASK>
 __global__ void __launch_bounds__(PM_RX* PM_RY)
     k_correct_rows(const __grid_constant__ KP k, const double* __restrict__ us, const double* __restrict__ vs,
-                   const double* __restrict__ p, double* __restrict__ u, double* __restrict__ v, int psplit) {
+                   const double* __restrict__ p, const uint8_t* __restrict__ M, double* __restrict__ u, double* __restrict__ v, int psplit) {
   const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x) + 1;
   const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
   if (i > k.nx || jl > k.nyl) return;
@@ -633,16 +580,23 @@ __global__ void __launch_bounds__(PM_RX* PM_RY)
   }
   const bool a_u = i <= k.nx - 1, b_u = i + 1 <= k.nx - 1;
   const bool a_v = j <= k.ny - 1, b_v = a_v && i + 1 <= k.nx;
+  bool ua_on = true, ub_on = true, va_on = true, vb_on = true;
+  if (MASK) {
+    const uchar2 mc = *reinterpret_cast<const uchar2*>(M + c), mn = *reinterpret_cast<const uchar2*>(M + c + P);
+    const uint8_t me2 = M[c + 2];
+    ua_on = (i == k.nx - 1) || mc.x || mc.y; ub_on = (i + 1 == k.nx - 1) || mc.y || me2;
+    va_on = (j == k.ny - 1) || mc.x || mn.x; vb_on = (j == k.ny - 1) || mc.y || mn.y;
+  }
   if (a_u) {
     const double2 U = ld2(us + c);
-    const double ua = A::sub(U.x, A::mul(k.cu, A::sub(pb, pa)));
-    if (b_u) st2(u + c, ua, A::sub(U.y, A::mul(k.cu, A::sub(pe2, pb))));
+    const double ua = ua_on ? A::sub(U.x, A::mul(k.cu, A::sub(pb, pa))) : 0.0;
+    if (b_u) st2(u + c, ua, ub_on ? A::sub(U.y, A::mul(k.cu, A::sub(pe2, pb))) : 0.0);
     else u[c] = ua;
   }
   if (a_v) {
     const double2 V = ld2(vs + c);
-    const double va = A::sub(V.x, A::mul(k.cv, A::sub(pna, pa)));
-    if (b_v) st2(v + c, va, A::sub(V.y, A::mul(k.cv, A::sub(pnb, pb))));
+    const double va = va_on ? A::sub(V.x, A::mul(k.cv, A::sub(pna, pa))) : 0.0;
+    if (b_v) st2(v + c, va, vb_on ? A::sub(V.y, A::mul(k.cv, A::sub(pnb, pb))) : 0.0);
     else v[c] = va;
   }
 }

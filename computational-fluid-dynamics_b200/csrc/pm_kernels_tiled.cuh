@@ -733,7 +733,7 @@ template <class A, int FORM, int METHOD, int T, int PAR0>
 __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t* bar, uint32_t phase, unsigned long long* red,
                                              double* __restrict__ pout, const double* __restrict__ f, PpeState* __restrict__ st,
                                              unsigned long long* __restrict__ res_bits, unsigned long long* __restrict__ fold_part, int m0, int nsw, int bx, int by,
-                                             int crank, uint64_t* xbar, const int* xact, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ tcls,
+                                             int crank, uint64_t* xbar, const int* xact, const uint8_t* __restrict__ mask, int tclass,
                                              const StopWords<T>& stopw, bool check_stop) {
   using C = TileCfg<METHOD, T>;
   constexpr int H = C::H, SW = C::SW, SH = C::SH, RPT = C::RPT, TX = C::TX, TY = C::TY, CS = C::CS;
@@ -817,8 +817,8 @@ __device__ __forceinline__ void tile_process(const KP& k, double* tile, uint64_t
   PM_PROF(1);  // wait for the TMA tile
   // Obstacle mask (step case): tiles with solid cells take their own path; the classes were computed with the mask.
   bool masked = false;
-  if constexpr (FORM == 1 && METHOD == PM_PPE_SOR_RB && CS == 1) if (tcls != nullptr) {
-    const int cls = tcls[by * int(gridDim.x) + bx];  // 0: fluid cells only, 1: no fluid cell, 2: both
+  if constexpr (FORM == 1 && METHOD == PM_PPE_SOR_RB && CS == 1) {
+    const int cls = tclass;
     if (cls != 0) {
       const MaskedGeom g{ib, jb, jI_lo, jI_hi, max(1, y0), min(k.nyl, y0 + TY - 1), max(1, x0), min(k.nx, x0 + TX - 1)};
       masked_tile<A, METHOD, T>(k, tile, f, mask, pout, red, g, m0, nsw, cls);
@@ -899,7 +899,7 @@ __global__ void __launch_bounds__((TileCfg<METHOD, T>::THREADS), PM_TILE_MINBLOC
     k_ppe_tiled(const __grid_constant__ KP k, const __grid_constant__ CUtensorMap tmap_in, double* __restrict__ pout,
                 const double* __restrict__ f, PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits,
                 unsigned long long* __restrict__ fold_part, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ tcls,
-                int m0, int nsw, int force, int tile_row0) {
+                const int* __restrict__ torder, int m0, int nsw, int force, int tile_row0) {
   using C = TileCfg<METHOD, T>;
   constexpr int CS = C::CS;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -914,7 +914,16 @@ __global__ void __launch_bounds__((TileCfg<METHOD, T>::THREADS), PM_TILE_MINBLOC
   // slower than interior tiles) starts in the first wave instead of forming the tail
   const int ncy = int(gridDim.y) / CS, cy = int(blockIdx.y) / CS;
   const int crank = CS > 1 ? int(cluster_ctarank()) : 0;
-  const int bx = blockIdx.x, by = tile_row0 + (cy == 0 ? ncy - 1 : cy - 1);
+  int bx = blockIdx.x, by = tile_row0 + (cy == 0 ? ncy - 1 : cy - 1);
+  int tclass = 0;  // obstacle mask: 0 fluid cells only, 1 no fluid cell, 2 both
+  if (CS == 1 && torder != nullptr) {  // whole-grid launch: the slow tiles (fluid and solid cells) first, the copied ones last
+    const int t = torder[blockIdx.y * gridDim.x + blockIdx.x];  // tile index | class << 28: one dependent load before the TMA can go out
+    tclass = t >> 28;
+    by = (t & 0x0fffffff) / int(gridDim.x);
+    bx = (t & 0x0fffffff) - by * int(gridDim.x);
+  } else if (CS == 1 && tcls != nullptr) {
+    tclass = tcls[by * int(gridDim.x) + bx];  // in flight during the tile load
+  }
 #ifdef PM_TILE_PROFILE
   const long long prof_k = clock64();
 #endif
@@ -954,7 +963,7 @@ __global__ void __launch_bounds__((TileCfg<METHOD, T>::THREADS), PM_TILE_MINBLOC
 #ifdef PM_TILE_PROFILE
   if (tid == 0) atomicAdd(&g_tile_prof[5], (unsigned long long)(clock64() - prof_k));
 #endif
-  tile_process<A, FORM, METHOD, T, PAR0>(k, tile, &mbar, 0u, red, pout, f, st, res_bits, fold_part, m0, nsw, bx, by, crank, xbar, xact, mask, tcls, stopw, !force);
+  tile_process<A, FORM, METHOD, T, PAR0>(k, tile, &mbar, 0u, red, pout, f, st, res_bits, fold_part, m0, nsw, bx, by, crank, xbar, xact, mask, tclass, stopw, !force);
 }
 
 // Whole-plane conversion between the natural and the split-row layout (a permutation inside every row).
@@ -998,6 +1007,7 @@ struct TiledPlan {
   size_t fold_bytes = 0;
   const uint8_t* mask = nullptr;        // obstacle mask plane (step case), else null
   uint8_t* tile_class = nullptr;        // per output block: 0 fluid cells only, 1 no fluid cell, 2 both (step case), else null
+  int* tile_order = nullptr;            // launch order of the output blocks of a whole-grid launch: class 2, then 0, then 1
 };
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1084,8 +1094,10 @@ static inline bool tiled_create(TiledPlan* pl, const pm_config& c, const KP& k, 
 static inline void tiled_destroy(TiledPlan* pl) {
   if (pl->fold_part) cudaFree(pl->fold_part);
   if (pl->tile_class) cudaFree(pl->tile_class);
+  if (pl->tile_order) cudaFree(pl->tile_order);
   pl->fold_part = nullptr;
   pl->tile_class = nullptr;
+  pl->tile_order = nullptr;
 }
 // Classes of the output blocks for an obstacle mask (global array, (ny+2) x (nx+2) bytes): looked at over the whole
 // tile around each block, ring included, clipped to the interior cells this rank has data for.
@@ -1107,9 +1119,16 @@ static inline bool tiled_classify(TiledPlan* pl, const KP& k, const uint8_t* glo
       }
       cls[size_t(by) * pl->tiles_x + bx] = !any_solid ? 0 : (!any_fluid ? 1 : 2);
     }
+  std::vector<int> order;
+  order.reserve(size_t(ntiles));
+  for (int want : {2, 0, 1})
+    for (int t = 0; t < ntiles; ++t)
+      if (cls[size_t(t)] == want) order.push_back(t | (want << 28));
   cudaError_t e = cudaSuccess;
   if (!pl->tile_class) e = cudaMalloc(&pl->tile_class, size_t(ntiles));
+  if (e == cudaSuccess && !pl->tile_order) e = cudaMalloc(&pl->tile_order, size_t(ntiles) * sizeof(int));
   if (e == cudaSuccess) e = cudaMemcpyAsync(pl->tile_class, cls.data(), size_t(ntiles), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pl->tile_order, order.data(), size_t(ntiles) * sizeof(int), cudaMemcpyHostToDevice, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   if (e != cudaSuccess) { *err = std::string("tile classes: ") + cudaGetErrorString(e); return false; }
   return true;
@@ -1123,8 +1142,9 @@ static inline cudaError_t tiled_begin_solve(const TiledPlan* pl, cudaStream_t st
 static inline cudaError_t tiled_launch(const TiledPlan* pl, const KP& k, int in, const double* f, PpeState* st, unsigned long long* res,
                                        int m0, int nsw, int force, int tile_row0, int tile_rows, cudaStream_t stream) {
   double* pout = pl->p[in ^ 1];
+  const int* order = (tile_row0 == 0 && tile_rows == pl->tiles_y) ? pl->tile_order : nullptr;
   void* args[] = {(void*)&k, (void*)&pl->map[in], (void*)&pout, (void*)&f, (void*)&st, (void*)&res, (void*)&pl->fold_part,
-                  (void*)&pl->mask, (void*)&pl->tile_class, (void*)&m0, (void*)&nsw, (void*)&force, (void*)&tile_row0};
+                  (void*)&pl->mask, (void*)&pl->tile_class, (void*)&order, (void*)&m0, (void*)&nsw, (void*)&force, (void*)&tile_row0};
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3(pl->tiles_x, tile_rows * pl->cs);
   lc.blockDim = dim3(pl->threads);
