@@ -43,8 +43,8 @@ struct pm_solver {
   pm_config cfg{};
   KP kp{};
   int device = 0;
-  cudaStream_t stream = nullptr, comm_stream = nullptr;
-  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_halo = nullptr, ev_edge = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
+  cudaStream_t stream = nullptr, comm_stream = nullptr, edge_stream = nullptr;  // edge_stream: high priority, the slab's edge tile rows
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_halo = nullptr, ev_edge = nullptr, ev_pass = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
   bool step_timed = false;
   double last_step_ppe_ms = 0.0;
   size_t plane = 0;        // doubles per plane
@@ -252,10 +252,11 @@ static int destroy_impl(pm_solver* s) {
   if (s->d_partial) cudaFree(s->d_partial);
   if (s->h_state) cudaFreeHost(s->h_state);
   if (s->h_res) cudaFreeHost(s->h_res);
-  for (cudaEvent_t e : {s->ev_a, s->ev_b, s->ev_t0, s->ev_t1, s->ev_halo, s->ev_edge, s->ev_s0, s->ev_s1})
+  for (cudaEvent_t e : {s->ev_a, s->ev_b, s->ev_t0, s->ev_t1, s->ev_halo, s->ev_edge, s->ev_pass, s->ev_s0, s->ev_s1})
     if (e) cudaEventDestroy(e);
   if (s->stream) cudaStreamDestroy(s->stream);
   if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+  if (s->edge_stream) cudaStreamDestroy(s->edge_stream);
   delete s;
   return PM_OK;
 }
@@ -282,8 +283,13 @@ static int create_impl(pm_solver* s, const pm_config* cfg) {
 
   CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;  // numerically lowest = greatest priority
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&s->edge_stream, cudaStreamNonBlocking, hi));
+  }
   for (cudaEvent_t* e : {&s->ev_a, &s->ev_b, &s->ev_t0, &s->ev_t1, &s->ev_s0, &s->ev_s1}) CK(cudaEventCreate(e));
-  for (cudaEvent_t* e : {&s->ev_halo, &s->ev_edge}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  for (cudaEvent_t* e : {&s->ev_halo, &s->ev_edge, &s->ev_pass}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 
   s->rows_alloc = nyl + 2 + 2 * k.padr;
   s->plane = size_t(k.pitch) * size_t(s->rows_alloc);
@@ -853,17 +859,23 @@ static int tiled_pass(pm_solver* s, int in, int m0, int nsw, int force) {
       s->timing.kernel_launches++;
       if (nsw > 0) PMTRY(exchange_halo(s, pl.p[in ^ 1], pl.halo, s->stream));
     } else {
-      CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, 0, bot, s->stream));
-      CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, pl.tiles_y - top, top, s->stream));
+      // The edge tile rows go out on a high-priority stream and the interior rows on the main stream at the same time:
+      // the edge CTAs are scheduled first, the interior ones fill the rest of the machine (two edge launches alone would
+      // leave half of it idle), and the halo rows travel while the interior is still being swept.
+      CK(cudaEventRecord(s->ev_pass, s->stream));
+      CK(cudaStreamWaitEvent(s->edge_stream, s->ev_pass, 0));
+      CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, 0, bot, s->edge_stream));
+      CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, pl.tiles_y - top, top, s->edge_stream));
       s->timing.kernel_launches += 2;
+      CK(cudaEventRecord(s->ev_edge, s->edge_stream));
       if (nsw > 0) {
-        CK(cudaEventRecord(s->ev_edge, s->stream));
         CK(cudaStreamWaitEvent(s->comm_stream, s->ev_edge, 0));
         PMTRY(exchange_halo(s, pl.p[in ^ 1], pl.halo, s->comm_stream));
         CK(cudaEventRecord(s->ev_halo, s->comm_stream));
       }
       CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, bot, pl.tiles_y - bot - top, s->stream));
       s->timing.kernel_launches++;
+      CK(cudaStreamWaitEvent(s->stream, s->ev_edge, 0));
       if (nsw > 0) CK(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
     }
   }
