@@ -439,77 +439,72 @@ __device__ __forceinline__ void rb_half_lean(const KP& k, double* tpx, double* t
   }
 }
 
-// One Jacobi sweep: new values of both cells of every row from the previous iterate, staged in
-// registers until every thread has finished reading.
+// One Jacobi sweep from the shared-memory tile at (sx, sy) into the one at (dx, dy): neighbours in other threads are
+// read from the source tile, every thread writes all of its cells (new, or unchanged) to the destination tile, so one
+// barrier per sweep separates the iterates; the thread's own column is walked upwards with the old value of the row
+// below carried in two registers (no staging of a whole sweep in registers: that spilled).
 template <class A, int FORM, bool INT, class C>
-__device__ __forceinline__ void jacobi_sweep(const KP& k, double* tpx, double* tpy, Cells<C::RPT>& c, int i0, int jg0, unsigned mW, unsigned mOut,
-                                             bool colW0, bool colW1, bool commit, double& rmax_pre) {
+__device__ __forceinline__ void jacobi_sweep(const KP& k, const double* sx, const double* sy, double* dx, double* dy, Cells<C::RPT>& c, int i0, int jg0,
+                                             unsigned mW, unsigned mOut, bool colW0, bool colW1, bool commit, double& rmax_pre) {
   constexpr int SW = C::SW, RPT = C::RPT;
-  double n0[RPT], n1[RPT];
+  double o0 = 0.0, o1 = 0.0;  // previous iterate of the row below
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
     const int j = jg0 + r;
-    const double wl = tpy[r * SW - 1];
-    const double er = tpx[r * SW + 1];
+    const double c0 = c.p0[r], c1 = c.p1[r];
+    const double wl = sy[r * SW - 1];
+    const double er = sx[r * SW + 1];
     double pn0, pn1, ps0, ps1;
     if (r + 1 < RPT) { pn0 = c.p0[r + 1]; pn1 = c.p1[r + 1]; }
-    else { pn0 = tpx[(r + 1) * SW]; pn1 = tpy[(r + 1) * SW]; }
-    if (r >= 1) { ps0 = c.p0[r - 1]; ps1 = c.p1[r - 1]; }
-    else { ps0 = tpx[(r - 1) * SW]; ps1 = tpy[(r - 1) * SW]; }
-    const double r0v = cell_residual<A, FORM, INT>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0v(r));
-    const double r1v = cell_residual<A, FORM, INT>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1v(r));
+    else { pn0 = sx[(r + 1) * SW]; pn1 = sy[(r + 1) * SW]; }
+    if (r >= 1) { ps0 = o0; ps1 = o1; }
+    else { ps0 = sx[(r - 1) * SW]; ps1 = sy[(r - 1) * SW]; }
+    const double r0v = cell_residual<A, FORM, INT>(k, j, i0, c0, c1, wl, pn0, ps0, c.f0v(r));
+    const double r1v = cell_residual<A, FORM, INT>(k, j, i0 + 1, c1, er, c0, pn1, ps1, c.f1v(r));
     acc_max(rmax_pre, r0v, (mOut >> r) & 1u);
     acc_max(rmax_pre, r1v, (mOut >> (16 + r)) & 1u);
+    o0 = c0; o1 = c1;
+    if (!commit) continue;  // the residual-only pass (uniform across the block)
+    double n0, n1;
     if (INT && !A::exact) {  // residual form of the relaxation, see rb_half
-      n0[r] = fma(k.cw, r0v, c.p0[r]);
-      n1[r] = fma(k.cw, r1v, c.p1[r]);
+      n0 = fma(k.cw, r0v, c0);
+      n1 = fma(k.cw, r1v, c1);
     } else {
-      n0[r] = cell_update<A, FORM, INT>(k, j, i0, c.p0[r], c.p1[r], wl, pn0, ps0, c.f0v(r));
-      n1[r] = cell_update<A, FORM, INT>(k, j, i0 + 1, c.p1[r], er, c.p0[r], pn1, ps1, c.f1v(r));
+      n0 = cell_update<A, FORM, INT>(k, j, i0, c0, c1, wl, pn0, ps0, c.f0v(r));
+      n1 = cell_update<A, FORM, INT>(k, j, i0 + 1, c1, er, c0, pn1, ps1, c.f1v(r));
+      if (!INT) {
+        const bool rowW = (mW >> r) & 1u;
+        if (!(rowW && colW0)) n0 = c0;
+        if (!(rowW && colW1)) n1 = c1;
+      }
     }
+    c.p0[r] = n0; c.p1[r] = n1;
+    dx[r * SW] = n0;
+    dy[r * SW] = n1;
   }
-  if (!commit) return;  // uniform across the block
-  __syncthreads();      // every neighbour value of the old iterate has been read
-  if (INT) {
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      c.p0[r] = n0[r];
-      c.p1[r] = n1[r];
-      tpx[r * SW] = n0[r];
-      tpy[r * SW] = n1[r];
-    }
-    __syncthreads();
-    return;
-  }
-#pragma unroll
-  for (int r = 0; r < RPT; ++r) {
-    const bool rowW = (mW >> r) & 1u;
-    if (rowW && colW0) { c.p0[r] = n0[r]; tpx[r * SW] = n0[r]; }
-    if (rowW && colW1) { c.p1[r] = n1[r]; tpy[r * SW] = n1[r]; }
-    if (FORM == 1 && rowW) {  // wall ghosts from the new values
-      if (colW0 && i0 == 1) tpy[r * SW - 1] = n0[r];
-      if (colW0 && i0 == k.nx) { tpy[r * SW] = 0.0; c.p1[r] = 0.0; }
-      if (colW1 && i0 + 1 == k.nx) tpx[r * SW + 1] = 0.0;
-    }
-  }
-  if (FORM == 1) {
-    // row ghosts: after all new values are in place (a ghost row register may belong to this thread)
+  if (!commit) return;
+  __syncthreads();  // the destination tile holds the new iterate (wall ghosts still the old ones)
+  if (FORM == 1 && !INT) {
+    // wall ghosts from the new values (channel-01.cpp:531-541), written by the thread that owns the wall-adjacent cell;
+    // then every thread takes its cells back from the tile (a ghost may be one of them)
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
       const int j = jg0 + r;
       const bool rowW = (mW >> r) & 1u;
       if (!rowW) continue;
-      if (j == 1) {
-        if (colW0) { tpx[(r - 1) * SW] = n0[r]; if (r >= 1) c.p0[r - 1] = n0[r]; }
-        if (colW1) { tpy[(r - 1) * SW] = n1[r]; if (r >= 1) c.p1[r - 1] = n1[r]; }
-      }
-      if (j == k.ny) {
-        if (colW0) { tpx[(r + 1) * SW] = n0[r]; if (r + 1 < RPT) c.p0[r + 1] = n0[r]; }
-        if (colW1) { tpy[(r + 1) * SW] = n1[r]; if (r + 1 < RPT) c.p1[r + 1] = n1[r]; }
-      }
+      if (colW0 && i0 == 1) dy[r * SW - 1] = c.p0[r];
+      if (colW0 && i0 == k.nx) dy[r * SW] = 0.0;
+      if (colW1 && i0 + 1 == k.nx) dx[r * SW + 1] = 0.0;
+      if (j == 1) { if (colW0) dx[(r - 1) * SW] = c.p0[r]; if (colW1) dy[(r - 1) * SW] = c.p1[r]; }
+      if (j == k.ny) { if (colW0) dx[(r + 1) * SW] = c.p0[r]; if (colW1) dy[(r + 1) * SW] = c.p1[r]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      c.p0[r] = dx[r * SW];
+      c.p1[r] = dy[r * SW];
     }
   }
-  __syncthreads();
 }
 
 // All sweeps of one pass for one thread.  The sweep loop is NOT unrolled (the instruction footprint of
@@ -552,7 +547,8 @@ __device__ __forceinline__ void run_sweeps(const KP& k, double* tpx, double* tpy
         }
       }
     } else {
-      jacobi_sweep<A, FORM, INT, C>(k, tpx, tpy, c, i0, jg0, mW, mOut, colW0, colW1, commit, r_cur);
+      const int so = (t & 1) * C::TILE_DOUBLES, dof = C::TILE_DOUBLES - so;  // the two tiles take turns
+      jacobi_sweep<A, FORM, INT, C>(k, tpx + so, tpy + so, tpx + dof, tpy + dof, c, i0, jg0, mW, mOut, colW0, colW1, commit, r_cur);
     }
     const double v = warp_max_nonneg(r_cur);
     if (lane == 0) redw[t] = (unsigned long long)__double_as_longlong(v);
@@ -1055,7 +1051,8 @@ static const void* tiled_pick(int method, int T, int par0, TiledPlan* pl) {
 
 static inline bool tiled_create(TiledPlan* pl, const pm_config& c, const KP& k, double* p0, double* p1, int rows_alloc, std::string* err) {
   // measured at 8192^2: production red-black 13.8 ms/step at T = 4 (14.6 at 3); exact arithmetic 22.3 at T = 3 (23.6 at 4)
-  int T = c.sweeps_per_pass > 0 ? c.sweeps_per_pass : (c.ppe_method == PM_PPE_SOR_RB ? (c.exact_arith ? 3 : 4) : 2);
+  // measured at 8192^2, Jacobi on 32 x 128 tiles, two shared-memory tiles: 13.6 ms/step at T = 4 (17.6 at T = 2)
+  int T = c.sweeps_per_pass > 0 ? c.sweeps_per_pass : (c.ppe_method == PM_PPE_SOR_RB ? (c.exact_arith ? 3 : 4) : 4);
   const bool masked = c.case_id == PM_CASE_STEP;
   if (masked) T = c.sweeps_per_pass > 0 ? std::min(4, c.sweeps_per_pass + 1) : 4;  // geometry one sweep deeper than what a pass runs
   const bool cav = c.case_id == PM_CASE_CAVITY;

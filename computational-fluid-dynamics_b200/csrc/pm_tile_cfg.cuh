@@ -6,7 +6,8 @@
 // Tile shape.  Red-black: 4 segments x 12 rows = 48 x 128 cells on 256 threads -- eight warps per CTA spread evenly
 // over the four SM sub-partitions (ten did not: 3/3/2/2), and the taller tile raises the share of output cells from
 // 63 % to 68 % at T = 3; it costs the full 128 registers per thread (96 hold the thread's 24 cells of p and f).
-// Jacobi stages a whole sweep of new values in registers and keeps 5 segments x 8 rows on 320 threads.
+// Jacobi sweeps from one shared-memory tile into a second one (no staging of new values in registers) on 4 segments x 8 rows
+// = 32 x 128 cells, 256 threads: 5 x 8 on 320 threads sat at the 96-register cap and spilled.
 #ifndef PM_TILE_NSEG
 #define PM_TILE_NSEG 4   // row segments per tile; 64 threads (column pairs) each
 #endif
@@ -14,7 +15,7 @@
 #define PM_TILE_RPT 12   // rows per thread (even: keeps the colour of a thread's first row uniform over the launch)
 #endif
 #ifndef PM_TILE_NSEG_JACOBI
-#define PM_TILE_NSEG_JACOBI 5
+#define PM_TILE_NSEG_JACOBI 4
 #endif
 #ifndef PM_TILE_RPT_JACOBI
 #define PM_TILE_RPT_JACOBI 8
@@ -45,7 +46,9 @@ struct TileCfg {
   static constexpr int TX = SW - 2 * H;           // output block of a cluster
   static constexpr int TY = CS * SH - 2 * H;
   static constexpr int XR = CS > 1 ? 1 : 0;       // rows below and above the tile that the TMA load brings along (the neighbour CTAs' edge rows)
-  static constexpr int SMEM_BYTES = (SH + 2) * SW * 8;  // tile + one row above and below (the neighbour CTA's edge row, or spare)
+  // tile + one row above and below (the neighbour CTA's edge row, or spare); Jacobi sweeps from one such tile into a second
+  static constexpr int TILE_DOUBLES = (SH + 2) * SW;
+  static constexpr int SMEM_BYTES = ((METHOD == PM_PPE_SOR_RB) ? 1 : 2) * TILE_DOUBLES * 8;
   static_assert(TX > 0 && TY > 0, "halo too deep for the tile");
   static_assert(CS >= 1 && CS <= 8, "portable cluster sizes only");
   static_assert(RPT % 2 == 0 && TY % 2 == 0, "PAR0 (colour of a thread's first row) must not depend on the segment or the tile row");
