@@ -363,11 +363,12 @@ __global__ void __launch_bounds__(1024, 1)
 // ---------------------------------------------------------------------------
 // Small grids, red-black, on a thread-block CLUSTER: the same persistent solve spread over 8 SMs.
 // CTA c of the cluster owns a band of rows of p and f in its own shared memory plus one halo row above and
-// below; after each colour half-sweep the CTAs meet at a cluster barrier (barrier.cluster, ~0.2 us) and every
-// CTA copies the freshly updated colour of its two halo rows straight out of its neighbours' shared memory
-// (distributed shared memory).  Only the other colour is being written at that time, so one cluster barrier
-// per half-sweep suffices.  The per-CTA residual maxima are exchanged the same way and every CTA evaluates the
-// reference's loop test (cavity-01.cpp:635) on the same number, so the cluster leaves the loop together.
+// below; after each colour half-sweep every CTA pushes the freshly updated colour of its first and last row straight
+// into its neighbours' halo rows (distributed shared memory: st.async, counted on an mbarrier of the receiving CTA)
+// and waits for its own halo rows to arrive -- no cluster barrier inside the loop (barrier.cluster's release costs a
+// MEMBAR.GPU: the pull-based version spent 3.7 us per iteration in three of them).  The per-CTA residual maxima travel
+// the same way to all eight CTAs, and every CTA evaluates the reference's loop test (cavity-01.cpp:635) on the same
+// number, so the cluster leaves the loop together.
 // ---------------------------------------------------------------------------
 #include <cooperative_groups.h>
 namespace pm_cg = cooperative_groups;
@@ -388,7 +389,9 @@ __global__ void __launch_bounds__(512, 1)
                   PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits) {
   extern __shared__ double smem[];
   __shared__ double red[32];
-  __shared__ double slot[2];  // this CTA's residual maximum, double-buffered by iteration parity
+  __shared__ __align__(16) double rslot[2][PM_CLUSTER];  // the eight CTAs' residual maxima, double-buffered by iteration parity
+  __shared__ __align__(8) uint64_t hbar[3][2];           // halo rows arrived: [exchange: colour 0, colour 1, every cell][from below, from above]
+  __shared__ __align__(8) uint64_t rbar[2];              // residual maxima arrived, by iteration parity
   pm_cg::cluster_group cluster = pm_cg::this_cluster();
   const int c = int(cluster.block_rank());
   const int nx = k.nx, ny = k.ny, PP = nx + 2;
@@ -400,11 +403,31 @@ __global__ void __launch_bounds__(512, 1)
     const int l = idx / PP, i = idx - l * PP;
     P[idx] = pg[pm_idx(k, j0 + l, i)];
   }
-  // neighbours' tiles through distributed shared memory
-  const double* Pdn = c > 0 ? cluster.map_shared_rank(P, c - 1) : nullptr;
-  const double* Pup = c + 1 < PM_CLUSTER ? cluster.map_shared_rank(P, c + 1) : nullptr;
+  const bool has_dn = c > 0, has_up = c + 1 < PM_CLUSTER;
   int nr_dn = 0, jdummy;
-  if (c > 0) pm_band(ny, c - 1, &jdummy, &nr_dn);
+  if (has_dn) pm_band(ny, c - 1, &jdummy, &nr_dn);
+  // Where this CTA's edge rows land: the lower neighbour's local row nr_dn + 1, the upper neighbour's local row 0.
+  const uint32_t p_dn = has_dn ? mapa_u32(smem_u32(P + size_t(nr_dn + 1) * PP), uint32_t(c - 1)) : 0u;
+  const uint32_t p_up = has_up ? mapa_u32(smem_u32(P), uint32_t(c + 1)) : 0u;
+  // cells of one colour in domain row j (kind 2: every cell), times 8 bytes: what one exchange delivers per direction
+  auto row_bytes = [&](int kind, int j) -> uint32_t {
+    if (kind == 2) return uint32_t(nx) * 8u;
+    const int first = 1 + ((kind + j + 1) & 1);  // first i >= 1 with (i + j) % 2 == kind
+    return uint32_t((nx - first) / 2 + 1) * 8u;
+  };
+  constexpr int NKIND = MASK ? 3 : 2;
+  if (tid == 0) {
+    for (int kd = 0; kd < 3; ++kd) { mbar_init(&hbar[kd][0], 1); mbar_init(&hbar[kd][1], 1); }
+    mbar_init(&rbar[0], 1);
+    mbar_init(&rbar[1], 1);
+    fence_mbar_init();
+    for (int kd = 0; kd < NKIND; ++kd) {
+      if (has_dn) mbar_expect_tx(&hbar[kd][0], row_bytes(kd, j0));            // my local row 0 = domain row j0
+      if (has_up) mbar_expect_tx(&hbar[kd][1], row_bytes(kd, j0 + nr + 1));   // my local row nr+1
+    }
+    mbar_expect_tx(&rbar[0], PM_CLUSTER * 8);
+    mbar_expect_tx(&rbar[1], PM_CLUSTER * 8);
+  }
 
   // The cells this thread relaxes, fixed for the whole solve: per colour up to PM_CLUSTER_CPT cells with their
   // shared-memory offset, their (j, i) and their source value in registers, so an iteration is nothing but
@@ -428,18 +451,33 @@ __global__ void __launch_bounds__(512, 1)
         }
       }
     }
-  cluster.sync();
+  cluster.sync();  // every CTA's band is loaded and its barriers are armed: from here on the CTAs only push
 
-  // halo rows: local row 0 <- lower neighbour's top owned row; local row nr+1 <- upper neighbour's row 1.
-  auto pull_halo = [&](int colour /* -1: every cell */) {
+  // Halo rows by push (no cluster barrier in the loop): after a half-sweep every CTA writes the cells of that colour of
+  // its first and last row straight into the neighbours' halo rows (st.async, counted on the neighbour's mbarrier) and
+  // waits for its own halo rows to arrive.  One barrier per kind of exchange and direction: the bytes of iteration n + 1
+  // cannot arrive before phase n has completed, because the neighbour sends them only after it has received what this CTA
+  // sends later in iteration n (and the residual exchange closes every iteration).
+  auto exchange = [&](int kind, int it) {
+    __syncthreads();  // the half-sweep's values are in shared memory
     for (int t = tid; t < 2 * nx; t += nth) {
       const int up = t >= nx, i = 1 + (up ? t - nx : t);
-      const int j = up ? j0 + nr + 1 : j0;
-      if (colour >= 0 && ((i + j) & 1) != colour) continue;
-      if (!up && Pdn) P[i] = Pdn[size_t(nr_dn) * PP + i];
-      if (up && Pup) P[size_t(nr + 1) * PP + i] = Pup[size_t(PP) + i];
+      const int l = up ? nr : 1;
+      if (kind < 2 && ((i + j0 + l) & 1) != kind) continue;
+      const double v = P[size_t(l) * PP + i];
+      if (!up && has_dn) st_async_f64(p_dn + uint32_t(i) * 8u, v, mapa_u32(smem_u32(&hbar[kind][1]), uint32_t(c - 1)));
+      if (up && has_up) st_async_f64(p_up + uint32_t(i) * 8u, v, mapa_u32(smem_u32(&hbar[kind][0]), uint32_t(c + 1)));
     }
-    __syncthreads();
+    const uint32_t ph = uint32_t(it - 1) & 1u;
+    if (tid < 32) {  // one warp watches the barriers; the block barrier below passes what it has seen on to the others
+      if (has_dn) mbar_wait(&hbar[kind][0], ph);
+      if (has_up) mbar_wait(&hbar[kind][1], ph);
+    }
+    __syncthreads();  // both rows have arrived: safe to arm the next phase and to read them
+    if (tid == 0) {
+      if (has_dn) mbar_expect_tx(&hbar[kind][0], row_bytes(kind, j0));
+      if (has_up) mbar_expect_tx(&hbar[kind][1], row_bytes(kind, j0 + nr + 1));
+    }
   };
   auto half_sweep = [&](int colour) {
 #pragma unroll
@@ -467,11 +505,9 @@ __global__ void __launch_bounds__(512, 1)
   while (res > tol && it < k.max_iters) {
     ++it;
     half_sweep(0);
-    cluster.sync();
-    pull_halo(0);
+    exchange(0, it);
     half_sweep(1);
-    cluster.sync();
-    pull_halo(1);
+    exchange(1, it);
     if (FORM == 1 && MASK) {  // backwards_step-01.cpp:685-740: wall ghosts first, then the solid cells
       for (int t = 1 + tid; t <= max(nx, nr); t += nth) {
         if (t <= nr) {
@@ -497,8 +533,7 @@ __global__ void __launch_bounds__(512, 1)
         if (j < ny && M[g + k.pitch]) { s = __dadd_rn(s, q[PP]); ++n; }
         if (n > 0) q[0] = __ddiv_rn(s, double(n));
       }
-      cluster.sync();
-      pull_halo(-1);  // solid cells of the neighbours' boundary rows changed too
+      exchange(2, it);  // solid cells of the neighbours' boundary rows changed too
     }
     double a = 0.0;
 #pragma unroll
@@ -513,14 +548,29 @@ __global__ void __launch_bounds__(512, 1)
                                    : res_channel<A>(k, qd[0], qd[1], qd[-1], qd[PP], qd[-PP], fv[colour][q]);
         a = fmax(a, fabs(r));
       }
-    const double m = block_max(a, red);
-    if (tid == 0) slot[it & 1] = m;
-    cluster.sync();
-    double g = 0.0;
-    if ((tid & 31) < PM_CLUSTER) g = cluster.map_shared_rank(slot, tid & 31)[it & 1];
-    res = warp_max(g);  // every warp reads the 8 maxima itself, so all threads of the cluster see the same number
+    // the maximum over the cluster: every CTA pushes its own into the slot array of all eight (itself included)
+    // two REDUX per warp (pm_kernels_tiled.cuh: warp_max_nonneg) instead of five rounds of 64-bit shuffles
+    const int b = it & 1;
+    {
+      const double wm = warp_max_nonneg(a);
+      if ((tid & 31) == 0) red[tid >> 5] = wm;
+      __syncthreads();
+      if (tid < 32) {
+        const double v = warp_max_nonneg(tid < (nth >> 5) ? red[tid] : 0.0);
+        if (tid == 0) red[0] = v;
+      }
+      __syncthreads();
+    }
+    if (tid < PM_CLUSTER)
+      st_async_f64(mapa_u32(smem_u32(&rslot[b][c]), uint32_t(tid)), red[0], mapa_u32(smem_u32(&rbar[b]), uint32_t(tid)));
+    if (tid < 32) mbar_wait(&rbar[b], uint32_t((it - 1) >> 1) & 1u);
+    __syncthreads();
+    const double g = (tid & 31) < PM_CLUSTER ? rslot[b][tid & 31] : 0.0;
+    res = warp_max_nonneg(g);  // every warp reads the 8 maxima itself, so all threads of the cluster see the same number
+    __syncthreads();    // every thread has read the slots: arm their next use (two iterations on)
+    if (tid == 0) mbar_expect_tx(&rbar[b], PM_CLUSTER * 8);
   }
-  cluster.sync();  // nobody leaves while a neighbour may still read this CTA's shared memory
+  cluster.sync();  // nobody leaves while a neighbour may still be pushing into this CTA's shared memory
 
   // write back the band, the wall-ghost columns, and the ghost rows the first / last CTA own
   const int la = c == 0 ? 0 : 1, lb = c == PM_CLUSTER - 1 ? nr + 1 : nr;
