@@ -17,6 +17,7 @@
 #include "pm_common.cuh"
 #include "pm_kernels_simple.cuh"
 #include "pm_kernels_tiled.cuh"
+#include "pm_kernels_stream.cuh"
 #include "pm_kernels_lex.cuh"
 #include "pm_nccl.hpp"
 
@@ -72,6 +73,9 @@ struct pm_solver {
   bool no_cluster = false; // PM_NO_CLUSTER=1 in the environment: keep the persistent solve on one SM
   int sweeps = 1;
   TiledPlan tiled{};
+  // streaming pass (pm_kernels_stream.cuh) over the interior tiles of the plan; f in the split-row layout for it
+  StreamPlan splan{};
+  double* fsplit = nullptr;
   PmNccl nccl{};
   pm_timing timing{};
   HostPipe hp{};
@@ -246,6 +250,8 @@ static int destroy_impl(pm_solver* s) {
   }
   if (s->base) cudaFree(s->base);
   if (s->tp[0]) cudaFree(s->tp[0]);
+  if (s->fsplit) cudaFree(s->fsplit);
+  stream_destroy(&s->splan);
   if (s->mask) cudaFree(s->mask);
   if (s->d_state) cudaFree(s->d_state);
   if (s->d_res) cudaFree(s->d_res);
@@ -259,6 +265,18 @@ static int destroy_impl(pm_solver* s) {
   if (s->edge_stream) cudaStreamDestroy(s->edge_stream);
   delete s;
   return PM_OK;
+}
+
+// Slabs: the tile rows whose output the neighbour slabs need within one pass (row 0, and as many rows from the top as cover
+// the last H output rows) are launched ahead of the rest.  A single rank has none.
+static void slab_edge_rows(const pm_solver* s, int* bot, int* top) {
+  *bot = *top = 0;
+  if (s->cfg.nranks == 1) return;
+  const TiledPlan& pl = s->tiled;
+  int t = 1;
+  while (t < pl.tiles_y && s->kp.nyl - (pl.tiles_y - t) * pl.ty < pl.halo) ++t;
+  *bot = 1;
+  *top = t;
 }
 
 static int create_impl(pm_solver* s, const pm_config* cfg) {
@@ -335,6 +353,13 @@ static int create_impl(pm_solver* s, const pm_config* cfg) {
       return fail(s, PM_ERR_CUDA, "tiled path setup: %s", e.c_str());
     s->sweeps = s->tiled.run;
     s->kp.psh = s->tiled.psh;
+    if (stream_supported(c, s->kp, s->tiled)) {
+      int bot = 0, top = 0;
+      slab_edge_rows(s, &bot, &top);
+      if (bot + top < s->tiled.tiles_y && !stream_create(&s->splan, s->tiled, c, s->kp, bot, s->tiled.tiles_y - top, s->stream, &e))
+        return fail(s, PM_ERR_CUDA, "streaming pass setup: %s", e.c_str());
+      if (s->splan.on) CK(cudaMalloc(&s->fsplit, s->plane * sizeof(double)));
+    }
   }
 
   // is_fluid: interior true; step: the reference rectangle (backwards_step-01.cpp:500-520).  After the kernel path is
@@ -845,39 +870,53 @@ static int read_state(pm_solver* s) {
 static int tiled_pass(pm_solver* s, int in, int m0, int nsw, int force) {
   const KP& k = s->kp;
   const TiledPlan& pl = s->tiled;
+  const StreamPlan& sp = s->splan;
   const double* f = s->pl[PL_F];
-  if (s->cfg.nranks == 1) {
-    CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, 0, pl.tiles_y, s->stream));
-    s->timing.kernel_launches++;
-  } else {
-    // edge tile rows: row 0, and as many rows from the top as cover the last H output rows
-    int top = 1;
-    while (top < pl.tiles_y && k.nyl - (pl.tiles_y - top) * pl.ty < pl.halo) ++top;
-    const int bot = 1;
-    if (bot + top >= pl.tiles_y) {
-      CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, 0, pl.tiles_y, s->stream));
-      s->timing.kernel_launches++;
-      if (nsw > 0) PMTRY(exchange_halo(s, pl.p[in ^ 1], pl.halo, s->stream));
-    } else {
-      // The edge tile rows go out on a high-priority stream and the interior rows on the main stream at the same time:
-      // the edge CTAs are scheduled first, the interior ones fill the rest of the machine (two edge launches alone would
-      // leave half of it idle), and the halo rows travel while the interior is still being swept.
+  // A full pass of production red-black: the interior tiles go to the streaming kernel, the frame around them (tiles at a
+  // wall) to k_ppe_tiled on the high-priority stream, both at once.
+  const bool streamed = sp.on && nsw == pl.sweeps;
+  int bot = 0, top = 0;
+  slab_edge_rows(s, &bot, &top);
+  if (s->cfg.nranks == 1 || bot + top >= pl.tiles_y) {
+    if (streamed && s->cfg.nranks == 1) {
       CK(cudaEventRecord(s->ev_pass, s->stream));
       CK(cudaStreamWaitEvent(s->edge_stream, s->ev_pass, 0));
-      CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, 0, bot, s->edge_stream));
-      CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, pl.tiles_y - top, top, s->edge_stream));
-      s->timing.kernel_launches += 2;
+      CK(tiled_launch_list(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, sp.frame, sp.nframe, s->edge_stream));
       CK(cudaEventRecord(s->ev_edge, s->edge_stream));
-      if (nsw > 0) {
-        CK(cudaStreamWaitEvent(s->comm_stream, s->ev_edge, 0));
-        PMTRY(exchange_halo(s, pl.p[in ^ 1], pl.halo, s->comm_stream));
-        CK(cudaEventRecord(s->ev_halo, s->comm_stream));
-      }
+      CK(stream_launch(&sp, &pl, k, in, s->fsplit, s->d_state, s->d_res, m0, force, s->stream));
+      CK(cudaStreamWaitEvent(s->stream, s->ev_edge, 0));
+      s->timing.kernel_launches += 2;
+    } else {
+      CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, 0, pl.tiles_y, s->stream));
+      s->timing.kernel_launches++;
+    }
+    if (s->cfg.nranks > 1 && nsw > 0) PMTRY(exchange_halo(s, pl.p[in ^ 1], pl.halo, s->stream));
+  } else {
+    // The edge tile rows go out on a high-priority stream and the interior rows on the main stream at the same time:
+    // the edge CTAs are scheduled first, the interior ones fill the rest of the machine (two edge launches alone would
+    // leave half of it idle), and the halo rows travel while the interior is still being swept.
+    CK(cudaEventRecord(s->ev_pass, s->stream));
+    CK(cudaStreamWaitEvent(s->edge_stream, s->ev_pass, 0));
+    CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, 0, bot, s->edge_stream));
+    CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, pl.tiles_y - top, top, s->edge_stream));
+    s->timing.kernel_launches += 2;
+    CK(cudaEventRecord(s->ev_edge, s->edge_stream));
+    if (nsw > 0) {
+      CK(cudaStreamWaitEvent(s->comm_stream, s->ev_edge, 0));
+      PMTRY(exchange_halo(s, pl.p[in ^ 1], pl.halo, s->comm_stream));
+      CK(cudaEventRecord(s->ev_halo, s->comm_stream));
+    }
+    if (streamed) {  // the frame of the middle rows behind the edge rows on their stream, the rectangle on the main stream
+      CK(tiled_launch_list(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, sp.frame, sp.nframe, s->edge_stream));
+      CK(cudaEventRecord(s->ev_edge, s->edge_stream));
+      CK(stream_launch(&sp, &pl, k, in, s->fsplit, s->d_state, s->d_res, m0, force, s->stream));
+      s->timing.kernel_launches += 2;
+    } else {
       CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, bot, pl.tiles_y - bot - top, s->stream));
       s->timing.kernel_launches++;
-      CK(cudaStreamWaitEvent(s->stream, s->ev_edge, 0));
-      if (nsw > 0) CK(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
     }
+    CK(cudaStreamWaitEvent(s->stream, s->ev_edge, 0));
+    if (nsw > 0) CK(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
   }
   // entries m0 .. m0+max(nsw,1)-1 are now complete on this rank (both colour parts): slots -> res_bits
   CK(tiled_fold_launch(&pl, k, s->d_res, m0, nsw, s->stream));
@@ -899,6 +938,7 @@ static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
     PMTRY(exchange_halo(s, s->pl[PL_F], pl.halo, s->stream));
     PMTRY(exchange_halo(s, pl.p[in0], pl.halo, s->stream));
   }
+  if (s->splan.on) PMTRY(convert_rows(s, s->pl[PL_F], s->fsplit, 1));  // f is constant over the solve
   int m = 0, n = 0;
   bool done = false;
   int chunk = s->cfg.poll_chunk > 0 ? s->cfg.poll_chunk : std::max(4, std::min(128, s->last_iters / (2 * T)));

@@ -22,15 +22,16 @@
 //     ((i + jl) even: (E + N) + (W + S), odd: (W + N) + (E + S)), so both kernels produce identical bits and can
 //     share one pass (k_ppe_tiled takes the frame of tiles that touch a wall or a slab edge).
 #pragma once
+#include <cstdio>
 #include "pm_kernels_tiled.cuh"
 
 #ifndef PM_STREAM_P
 #define PM_STREAM_P 3  // rows in flight beyond the row whose north neighbours the first half-sweep reads; the p ring holds P + 1 rows
 #endif
 #ifndef PM_STREAM_MINB
-#define PM_STREAM_MINB 10
+#define PM_STREAM_MINB 12
 #endif
-static_assert(PM_STREAM_P == 3 || PM_STREAM_P == 7, "the p ring (P + 1 rows) must divide the 8-tick unroll; the f ring holds 16 rows");
+static_assert(PM_STREAM_P == 3, "the p ring (P + 1 rows) must divide the 8-tick unroll; the f ring holds the 8 rows in flight and the P + 1 on their way: 12");
 
 struct StreamGeom {
   int bx0, nbx;  // first strip (tile column of the tiled plan) and number of strips
@@ -40,7 +41,8 @@ struct StreamGeom {
 };
 
 #define PM_STREAM_PRING_BYTES ((PM_STREAM_P + 1) * 1024)
-#define PM_STREAM_SMEM_BYTES (PM_STREAM_PRING_BYTES + 16 * 1024)
+#define PM_STREAM_FRING_ROWS 12
+#define PM_STREAM_SMEM_BYTES (PM_STREAM_PRING_BYTES + PM_STREAM_FRING_ROWS * 1024)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -53,19 +55,22 @@ struct StreamCtx {
   double r[8][4];   // rows in flight: slot = tick & 7, cells {E0, O0, E1, O1}
   double acc[8];    // max |r| seen by half-sweep h over the output cells of the chunk
   const double2* pr;  // this lane's 16 bytes in the p ring: row slot s at pr[s * 64], odd columns at + 32
-  const double2* fr;  // likewise in the f ring (16 rows)
-  int flo, fhi;       // f ring: index offset for the static slots below 8 / from 8 up (the ring is twice the unroll)
+  const double2* fr;  // likewise in the f ring (12 rows)
+  // f ring: row tau + d sits in slot (tau + d) mod 12; with tau = 8 * pass + U the slot of a static d = U - h (or U + 4 for
+  // the fetch) is fb[class of d] + d, where the class says on which side of the ring's end d falls for this pass
+  // (d in [-7,-5], [-4,-1], [0,3], [4,7], [8,11]); in units of double2 (64 per row)
+  int fb[5];
   uint32_t pdst, fdst;  // shared-space addresses of pr / fr for cp.async
   const double* pin;    // + element offset = the lane's even-column pair of a row; odd pair at + half
   const double* fin;
   double* pout;
-  size_t gsrc;   // element offset of the next row to fetch
-  size_t gdst;   // element offset of the row that leaves in this tick (row tau - 7)
+  uint32_t gsrc;  // element offset of the next row to fetch (planes stay below 2^32 elements: pm_create checks)
+  uint32_t gdst;  // element offset of the row that leaves in this tick (row tau - 7)
   int half;      // pitch / 2
   int pitch;
-  int tau;       // tick
+  int tau;       // tick (kept by the DYN ticks only)
   int rows;      // R: output rows of this chunk
-  int nfetch;    // rows still to fetch after the next one (the fetch pointer stops at the chunk's last row)
+  int nfetch;    // rows still to fetch (kept by the DYN ticks only)
   unsigned act;  // bit h: the row half-sweep h works on lies in the output rows and this lane holds output columns
   bool lane_ok;
 };
@@ -80,7 +85,20 @@ __device__ __forceinline__ double stream_res(const KP& k, double pc, double pw, 
   return res_sum22(k, pc, pw + pe, pn + ps, f);
 }
 
-template <int FORM, int PAR0, int U>
+// m = std::max(m, std::abs(x)) (a NaN never replaces m), branch-free: DSETP.GT with |x| folded in, FSEL |hi|, SEL lo.
+// (fmax() drags NaN quieting and register copies along; an `if` around two of these turns into branches.)
+__device__ __forceinline__ void stream_max(double& m, double x) {
+  asm("{\n .reg .pred q;\n .reg .f64 a;\n abs.f64 a, %1;\n setp.gt.f64 q, a, %0;\n selp.f64 %0, a, %0, q;\n}" : "+d"(m) : "d"(x));
+}
+__device__ __forceinline__ void stream_max_if(double& m, double x, unsigned on) {
+  asm("{\n .reg .pred q, o;\n .reg .f64 a;\n setp.ne.u32 o, %2, 0;\n abs.f64 a, %1;\n setp.gt.and.f64 q, a, %0, o;\n selp.f64 %0, a, %0, q;\n}"
+      : "+d"(m)
+      : "d"(x), "r"(on));
+}
+
+// DYN: the ticks at the two ends of a chunk, where some half-sweeps work on rows outside the output rows (bit h of c.act);
+// in between every half-sweep's row is an output row, and the lanes that hold halo columns are dropped at the very end.
+template <int FORM, int PAR0, int U, bool DYN>
 __device__ __forceinline__ void stream_tick(const KP& k, StreamCtx& c) {
   constexpr int P = PM_STREAM_P, PR = P + 1;
   constexpr bool tgtE = ((U + PAR0) & 1) == 0;  // this tick's half-sweeps all update the even storage columns (i odd) of their rows
@@ -94,7 +112,7 @@ __device__ __forceinline__ void stream_tick(const KP& k, StreamCtx& c) {
     c.r[U][1] = o.x; c.r[U][3] = o.y;
   }
   const double2 nx = c.pr[((U + 1) % PR) * 64 + (tgtE ? 0 : 32)];  // row tau + 1 as it came from HBM: north of half-sweep 0
-  c.act = ((c.act << 1) & 0xffu) | unsigned(c.lane_ok && unsigned(c.tau - 8) < unsigned(c.rows));
+  if (DYN) c.act = ((c.act << 1) & 0xffu) | unsigned(unsigned(c.tau - 8) < unsigned(c.rows));
   // the one neighbour per row that lives in another lane: none of these cells changes during this tick
   double xn[8];
 #pragma unroll
@@ -108,8 +126,8 @@ __device__ __forceinline__ void stream_tick(const KP& k, StreamCtx& c) {
     const int sl = (U - h) & 7, sn = (U - h + 1) & 7, ss = (U - h - 1) & 7;
     const bool jl_odd = ((U - h) & 1) == 0;               // the chunk's first row is odd
     const bool pair_a = tgtE ? jl_odd : !jl_odd;          // (i + jl) even
-    const int fs = (U - h) & 15;                          // static f slot; the ring's other half every second pass of the loop
-    const double2 fv = c.fr[(fs < 8 ? c.flo : c.fhi) + fs * 64 + (tgtE ? 0 : 32)];
+    const int d = U - h;
+    const double2 fv = c.fr[c.fb[d <= -5 ? 0 : d <= -1 ? 1 : d <= 3 ? 2 : 3] + d * 64 + (tgtE ? 0 : 32)];
     const double p0 = c.r[sl][G0], p1 = c.r[sl][G1];
     double w0, e0, w1, e1;
     if (tgtE) { w0 = xn[h]; e0 = c.r[sl][1]; w1 = c.r[sl][1]; e1 = c.r[sl][3]; }
@@ -126,31 +144,47 @@ __device__ __forceinline__ void stream_tick(const KP& k, StreamCtx& c) {
     }
     c.r[sl][G0] = fma(k.cw, r0, p0);
     c.r[sl][G1] = fma(k.cw, r1, p1);
-    const bool on = (c.act >> h) & 1u;
-    acc_max(c.acc[h], r0, on);
-    acc_max(c.acc[h], r1, on);
+    if (DYN) {
+      stream_max_if(c.acc[h], r0, c.act & (1u << h));
+      stream_max_if(c.acc[h], r1, c.act & (1u << h));
+    } else {
+      stream_max(c.acc[h], r0);
+      stream_max(c.acc[h], r1);
+    }
   }
   // row tau - 7 has passed all half-sweeps
-  if ((c.act >> 7) & 1u) {
+  if (c.lane_ok && (!DYN || ((c.act >> 7) & 1u))) {
     const int so = (U + 1) & 7;
     *reinterpret_cast<double2*>(c.pout + c.gdst) = make_double2(c.r[so][0], c.r[so][2]);
     *reinterpret_cast<double2*>(c.pout + c.gdst + c.half) = make_double2(c.r[so][1], c.r[so][3]);
   }
-  c.gdst += size_t(c.pitch);
-  // fetch row tau + P + 1 into the slots row tau (p) and row tau - 8 - (7 - P) (f) have left
+  c.gdst += uint32_t(c.pitch);
+  // fetch row tau + P + 1 into the slots row tau (p) and row tau - 8 (f) have left
   {
-    const int fs = (U + PR) & 15;
+    const int d = U + PR;
     const uint32_t pd = c.pdst + uint32_t((U % PR) * 1024);
-    const uint32_t fd = c.fdst + uint32_t(((fs < 8 ? c.flo : c.fhi) + fs * 64) * 16);
-    cp_async16(pd, c.pin + c.gsrc);
-    cp_async16(pd + 512u, c.pin + c.gsrc + c.half);
-    cp_async16(fd, c.fin + c.gsrc);
-    cp_async16(fd + 512u, c.fin + c.gsrc + c.half);
+    const uint32_t fd = c.fdst + uint32_t((c.fb[d <= 7 ? 3 : 4] + d * 64) * 16);
+    if (!DYN || c.nfetch > 0) {  // nothing beyond the chunk's last row is needed (or may exist)
+      cp_async16(pd, c.pin + c.gsrc);
+      cp_async16(pd + 512u, c.pin + c.gsrc + c.half);
+      cp_async16(fd, c.fin + c.gsrc);
+      cp_async16(fd + 512u, c.fin + c.gsrc + c.half);
+    }
     cp_async_commit();
-    if (c.nfetch > 0) c.gsrc += size_t(c.pitch);
-    --c.nfetch;
+    c.gsrc += uint32_t(c.pitch);
+    if (DYN) --c.nfetch;
   }
-  ++c.tau;
+  if (DYN) ++c.tau;
+}
+
+// Offsets of the five classes of d for the pass whose first tick sits in ring slot `base` (0, 8, 4, 0, ...).
+__device__ __forceinline__ void stream_fring_bases(StreamCtx& c, int base) {
+  constexpr int N = PM_STREAM_FRING_ROWS;
+  c.fb[0] = (base + (base <= 4 ? N : 0)) * 64;   // d in [-7,-5]: below slot 0 unless the pass starts at 8
+  c.fb[1] = (base + (base == 0 ? N : 0)) * 64;   // d in [-4,-1]
+  c.fb[2] = base * 64;                           // d in [0,3]
+  c.fb[3] = (base - (base == 8 ? N : 0)) * 64;   // d in [4,7]
+  c.fb[4] = (base - (base >= 4 ? N : 0)) * 64;   // d in [8,11]
 }
 
 template <int FORM, int PAR0>
@@ -181,7 +215,7 @@ __global__ void __launch_bounds__(32, PM_STREAM_MINB)
   }
   c.pr = reinterpret_cast<const double2*>(stream_smem) + lane;
   c.fr = reinterpret_cast<const double2*>(stream_smem + PM_STREAM_PRING_BYTES) + lane;
-  c.flo = c.fhi = 0;
+  stream_fring_bases(c, 0);
   c.pdst = smem_u32(c.pr);
   c.fdst = smem_u32(c.fr);
   c.pin = pin;
@@ -189,14 +223,14 @@ __global__ void __launch_bounds__(32, PM_STREAM_MINB)
   c.pout = pout;
   c.pitch = k.pitch;
   c.half = k.pitch >> 1;
-  c.gsrc = size_t(k.padr + jstart) * size_t(k.pitch) + size_t(pe);
-  c.gdst = size_t(k.padr + jstart - 7) * size_t(k.pitch) + size_t(pe);
+  c.gsrc = uint32_t(k.padr + jstart) * uint32_t(k.pitch) + uint32_t(pe);
+  c.gdst = uint32_t(k.padr + jstart - 7) * uint32_t(k.pitch) + uint32_t(pe);
   c.tau = 0;
   c.rows = yb - ya;
   c.act = 0u;
   c.lane_ok = lane >= 2 && lane <= 29;  // columns 8 .. 119 of the strip
   const int nrows = c.rows + 2 * H;      // rows that enter: the output rows and H below / above
-  c.nfetch = nrows - 1;
+  c.nfetch = nrows;
   // rows 0 .. P
 #pragma unroll
   for (int q = 0; q < PR; ++q) {
@@ -206,7 +240,7 @@ __global__ void __launch_bounds__(32, PM_STREAM_MINB)
     cp_async16(fd, c.fin + c.gsrc);
     cp_async16(fd + 512u, c.fin + c.gsrc + c.half);
     cp_async_commit();
-    if (c.nfetch > 0) c.gsrc += size_t(c.pitch);
+    c.gsrc += uint32_t(c.pitch);
     --c.nfetch;
   }
   if (!force) {  // the reference's loop test (uniform over the grid), as in k_ppe_tiled
@@ -220,21 +254,39 @@ __global__ void __launch_bounds__(32, PM_STREAM_MINB)
       return;
     }
   }
-  // tick tau: rows tau (+1 as north) must be there; the last output row leaves at tick rows + 14
+  // Tick tau needs rows tau and tau + 1; the last output row leaves at tick rows + 14.  Eight ticks per pass of the loop;
+  // passes 2 .. rows / 8 (ticks 16 .. rows + 7) have every half-sweep on an output row and every fetch inside the chunk.
   const int nticks = c.rows + 2 * H - 1;
+  const int nit = (nticks + 7) >> 3, it_steady_last = min(c.rows >> 3, nit - 1);
+  int fbase = 0;
 #pragma unroll 1
-  for (int it = 0; it * 8 < nticks; ++it) {
-    stream_tick<FORM, PAR0, 0>(k, c);
-    stream_tick<FORM, PAR0, 1>(k, c);
-    stream_tick<FORM, PAR0, 2>(k, c);
-    stream_tick<FORM, PAR0, 3>(k, c);
-    stream_tick<FORM, PAR0, 4>(k, c);
-    stream_tick<FORM, PAR0, 5>(k, c);
-    stream_tick<FORM, PAR0, 6>(k, c);
-    stream_tick<FORM, PAR0, 7>(k, c);
-    // the f ring holds 16 rows: every second pass of the loop works on its other half
-    c.flo = 512 - c.flo;
-    c.fhi = -c.flo;
+  for (int it = 0; it < nit; ++it) {
+    if (it >= 2 && it <= it_steady_last) {
+      stream_tick<FORM, PAR0, 0, false>(k, c);
+      stream_tick<FORM, PAR0, 1, false>(k, c);
+      stream_tick<FORM, PAR0, 2, false>(k, c);
+      stream_tick<FORM, PAR0, 3, false>(k, c);
+      stream_tick<FORM, PAR0, 4, false>(k, c);
+      stream_tick<FORM, PAR0, 5, false>(k, c);
+      stream_tick<FORM, PAR0, 6, false>(k, c);
+      stream_tick<FORM, PAR0, 7, false>(k, c);
+    } else {
+      if (it_steady_last >= 2 && it == it_steady_last + 1) {  // the steady passes do not keep the bits (all were set) nor the counters
+        c.act = 0xffu;
+        c.tau += 8 * (it_steady_last - 1);
+        c.nfetch -= 8 * (it_steady_last - 1);
+      }
+      stream_tick<FORM, PAR0, 0, true>(k, c);
+      stream_tick<FORM, PAR0, 1, true>(k, c);
+      stream_tick<FORM, PAR0, 2, true>(k, c);
+      stream_tick<FORM, PAR0, 3, true>(k, c);
+      stream_tick<FORM, PAR0, 4, true>(k, c);
+      stream_tick<FORM, PAR0, 5, true>(k, c);
+      stream_tick<FORM, PAR0, 6, true>(k, c);
+      stream_tick<FORM, PAR0, 7, true>(k, c);
+    }
+    fbase = fbase >= 4 ? fbase - 4 : fbase + 8;  // (fbase + 8) mod 12
+    stream_fring_bases(c, fbase);
   }
   cp_async_wait<0>();
   // per-iterate maxima: entry t = colour-0 part of iterate m0 + t (half-sweep 2t, operands before the update) and the
@@ -247,7 +299,7 @@ __global__ void __launch_bounds__(32, PM_STREAM_MINB)
       const double m = sc * c.acc[2 * t - 1];
       if (m > v) v = m;
     }
-    v = warp_max_nonneg(v);
+    v = warp_max_nonneg(c.lane_ok ? v : 0.0);  // the lanes of the strip's halo columns hold no output cell
     const int m = m0 + t;
     const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
     if (lane == 0 && bits != 0ull && m >= 1 && m <= k.max_iters)
@@ -255,7 +307,115 @@ __global__ void __launch_bounds__(32, PM_STREAM_MINB)
   }
 }
 
+#ifdef PM_TILED_DEVICE_ONLY
+template <int FORM>
+static const void* stream_kernel_ptr(int) { return reinterpret_cast<const void*>(&k_ppe_stream<FORM, 0>); }
+#else
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
 template <int FORM>
 static const void* stream_kernel_ptr(int par0) {
   return par0 ? reinterpret_cast<const void*>(&k_ppe_stream<FORM, 1>) : reinterpret_cast<const void*>(&k_ppe_stream<FORM, 0>);
 }
+
+// Which tiles of the tiled plan's rows [row_lo, row_hi) the streaming kernel takes (the largest rectangle of tiles that lie
+// strictly inside the domain with data for every neighbour: k_ppe_tiled's `interior`, which is separable in x and y),
+// and the list of the others for tiled_launch_list.
+struct StreamPlan {
+  bool on = false;
+  StreamGeom g{};
+  const void* kernel = nullptr;
+  int* frame = nullptr;
+  int nframe = 0;
+  int items = 0;
+};
+
+static inline void stream_destroy(StreamPlan* sp) {
+  if (sp->frame) cudaFree(sp->frame);
+  sp->frame = nullptr;
+  sp->on = false;
+}
+
+static inline bool stream_supported(const pm_config& c, const KP& k, const TiledPlan& pl) {
+  const int nyl_rows = k.nyl + 2 + 2 * k.padr;
+  return !c.exact_arith && c.ppe_method == PM_PPE_SOR_RB && !k.has_mask && pl.sweeps == 4 && pl.run == 4 && pl.cs == 1 &&
+         double(nyl_rows) * double(k.pitch) < 4.0e9 &&  // 32-bit element offsets inside a plane
+         std::getenv("PM_NO_STREAM") == nullptr;
+}
+
+static inline bool stream_create(StreamPlan* sp, const TiledPlan& pl, const pm_config& c, const KP& k, int row_lo, int row_hi, cudaStream_t stream,
+                                 std::string* err) {
+  sp->on = false;
+  const int H = pl.halo, SW = 128, SH = pl.sh;
+  auto x_ok = [&](int bx) { const int ib = 1 + bx * pl.tx - H; return ib + 1 >= 2 && ib + SW - 2 <= k.nx - 1; };
+  auto y_ok = [&](int by) {
+    const int jb = 1 + by * pl.ty - H;
+    return k.j0 + jb + 1 >= 2 && k.j0 + jb + SH - 2 <= k.ny - 1 && jb + SH - 1 <= k.nyl + H && jb >= 1 - H;
+  };
+  int bx0 = -1, bx1 = -2, by0 = -1, by1 = -2;
+  for (int bx = 0; bx < pl.tiles_x; ++bx)
+    if (x_ok(bx)) { if (bx0 < 0) bx0 = bx; bx1 = bx; }
+  for (int by = row_lo; by < row_hi; ++by)
+    if (y_ok(by)) { if (by0 < 0) by0 = by; by1 = by; }
+  // (both predicates hold on one contiguous range)
+  for (int bx = bx0; bx0 >= 0 && bx <= bx1; ++bx) if (!x_ok(bx)) { bx0 = -1; break; }
+  for (int by = by0; by0 >= 0 && by <= by1; ++by) if (!y_ok(by)) { by0 = -1; break; }
+  if (bx0 < 0 || by0 < 0) return true;  // nothing to stream: the tiled kernel keeps every tile
+  const int nbx = bx1 - bx0 + 1, nby = by1 - by0 + 1;
+  if (nbx * nby < 64) return true;
+  // chunk height: whole tile rows; few waves of warps over the machine, little of each chunk spent on its 16 halo rows
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int slots = sms * PM_STREAM_MINB, rows = nby * pl.ty;
+  int best = pl.ty;
+  double best_cost = 1e300;
+  for (int R = pl.ty; R <= 1024 && R <= ((rows + pl.ty - 1) / pl.ty) * pl.ty; R += pl.ty) {
+    const int nch = (rows + R - 1) / R;
+    const double waves = double((long long)nbx * nch + slots - 1) / slots;
+    const double cost = (waves < 1.0 ? 1.0 : waves) * (R + 2 * H + 8);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = R; }
+  }
+  if (const char* e = std::getenv("PM_STREAM_ROWS")) {
+    const int R = std::atoi(e);
+    if (R >= pl.ty && R % pl.ty == 0) best = R;
+  }
+  sp->g.bx0 = bx0; sp->g.nbx = nbx;
+  sp->g.ya = 1 + by0 * pl.ty; sp->g.ye = 1 + (by1 + 1) * pl.ty;
+  sp->g.rows = best;
+  sp->g.nchunks = (rows + best - 1) / best;
+  sp->items = nbx * sp->g.nchunks;
+  const bool cav = c.case_id == PM_CASE_CAVITY;
+  sp->kernel = cav ? stream_kernel_ptr<0>(k.j0 & 1) : stream_kernel_ptr<1>(k.j0 & 1);
+  cudaError_t e = cudaFuncSetAttribute(sp->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PM_STREAM_SMEM_BYTES);
+  if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(stream): ") + cudaGetErrorString(e); return false; }
+  std::vector<int> frame;
+  for (int by = row_lo; by < row_hi; ++by)
+    for (int bx = 0; bx < pl.tiles_x; ++bx)
+      if (!(bx >= bx0 && bx <= bx1 && by >= by0 && by <= by1)) frame.push_back(by * pl.tiles_x + bx);
+  sp->nframe = int(frame.size());
+  if (sp->frame) { cudaFree(sp->frame); sp->frame = nullptr; }
+  if (sp->nframe > 0) {
+    e = cudaMalloc(&sp->frame, frame.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sp->frame, frame.data(), frame.size() * sizeof(int), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { *err = std::string("stream plan: ") + cudaGetErrorString(e); return false; }
+  }
+  sp->on = true;
+  if (std::getenv("PM_DEBUG_STREAM"))
+    fprintf(stderr, "[pm] streaming pass: strips %d..%d, rows %d..%d in chunks of %d -> %d warps; %d frame tiles\n", bx0, bx1, sp->g.ya, sp->g.ye - 1,
+            sp->g.rows, sp->items, sp->nframe);
+  return true;
+}
+
+// One pass (T = 4 sweeps) over the plan's rectangle: reads iterate m0 from buffer `in`, writes iterate m0 + 4 to the other.
+static inline cudaError_t stream_launch(const StreamPlan* sp, const TiledPlan* pl, const KP& k, int in, const double* fsplit, PpeState* st,
+                                        unsigned long long* res, int m0, int force, cudaStream_t stream) {
+  const double* pin = pl->p[in];
+  double* pout = pl->p[in ^ 1];
+  void* args[] = {(void*)&k, (void*)&pin, (void*)&pout, (void*)&fsplit, (void*)&st, (void*)&res, (void*)&pl->fold_part, (void*)&sp->g, (void*)&m0, (void*)&force};
+  static_assert(PM_STREAM_SMEM_BYTES == 16 * 1024, "12 warps per SM");
+  return cudaLaunchKernel(sp->kernel, dim3(sp->items), dim3(32), args, PM_STREAM_SMEM_BYTES, stream);
+}
+#endif  // PM_TILED_DEVICE_ONLY

@@ -895,7 +895,7 @@ __global__ void __launch_bounds__((TileCfg<METHOD, T>::THREADS), PM_TILE_MINBLOC
     k_ppe_tiled(const __grid_constant__ KP k, const __grid_constant__ CUtensorMap tmap_in, double* __restrict__ pout,
                 const double* __restrict__ f, PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits,
                 unsigned long long* __restrict__ fold_part, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ tcls,
-                const int* __restrict__ torder, int m0, int nsw, int force, int tile_row0) {
+                const int* __restrict__ torder, int m0, int nsw, int force, int tile_row0, int order_ntx) {
   using C = TileCfg<METHOD, T>;
   constexpr int CS = C::CS;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -914,9 +914,10 @@ __global__ void __launch_bounds__((TileCfg<METHOD, T>::THREADS), PM_TILE_MINBLOC
   int tclass = 0;  // obstacle mask: 0 fluid cells only, 1 no fluid cell, 2 both
   if (CS == 1 && torder != nullptr) {  // whole-grid launch: the slow tiles (fluid and solid cells) first, the copied ones last
     const int t = torder[blockIdx.y * gridDim.x + blockIdx.x];  // tile index | class << 28: one dependent load before the TMA can go out
+    const int ntx = order_ntx > 0 ? order_ntx : int(gridDim.x);  // a list launch (tiled_launch_list) has its own grid shape
     tclass = t >> 28;
-    by = (t & 0x0fffffff) / int(gridDim.x);
-    bx = (t & 0x0fffffff) - by * int(gridDim.x);
+    by = (t & 0x0fffffff) / ntx;
+    bx = (t & 0x0fffffff) - by * ntx;
   } else if (CS == 1 && tcls != nullptr) {
     tclass = tcls[by * int(gridDim.x) + bx];  // in flight during the tile load
   }
@@ -984,6 +985,7 @@ __global__ void k_split_rows(const __grid_constant__ KP k, const double* __restr
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+#ifndef PM_TILED_DEVICE_ONLY  // (kernel experiments compile the device code alone)
 struct TiledPlan {
   int sweeps = 1;       // T: temporal-blocking depth the tile geometry (halo) was built for
   int run = 1;          // sweeps actually done per pass: T, or T - 1 with an obstacle mask (see masked_tile: the solid cells of the
@@ -1140,8 +1142,9 @@ static inline cudaError_t tiled_launch(const TiledPlan* pl, const KP& k, int in,
                                        int m0, int nsw, int force, int tile_row0, int tile_rows, cudaStream_t stream) {
   double* pout = pl->p[in ^ 1];
   const int* order = (tile_row0 == 0 && tile_rows == pl->tiles_y) ? pl->tile_order : nullptr;
+  int order_ntx = 0;
   void* args[] = {(void*)&k, (void*)&pl->map[in], (void*)&pout, (void*)&f, (void*)&st, (void*)&res, (void*)&pl->fold_part,
-                  (void*)&pl->mask, (void*)&pl->tile_class, (void*)&order, (void*)&m0, (void*)&nsw, (void*)&force, (void*)&tile_row0};
+                  (void*)&pl->mask, (void*)&pl->tile_class, (void*)&order, (void*)&m0, (void*)&nsw, (void*)&force, (void*)&tile_row0, (void*)&order_ntx};
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3(pl->tiles_x, tile_rows * pl->cs);
   lc.blockDim = dim3(pl->threads);
@@ -1154,6 +1157,18 @@ static inline cudaError_t tiled_launch(const TiledPlan* pl, const KP& k, int in,
   lc.numAttrs = pl->cs > 1 ? 1 : 0;
   return cudaLaunchKernelExC(&lc, pl->kernel, args);
 }
+// The same pass over an explicit list of n tiles (device array: tile index | class << 28), one CTA each: the frame of tiles
+// around the rectangle the streaming kernel takes (pm_kernels_stream.cuh).  Independent tiles only.
+static inline cudaError_t tiled_launch_list(const TiledPlan* pl, const KP& k, int in, const double* f, PpeState* st, unsigned long long* res,
+                                            int m0, int nsw, int force, const int* list, int n, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  if (pl->cs != 1) return cudaErrorInvalidValue;
+  double* pout = pl->p[in ^ 1];
+  int tile_row0 = 0, order_ntx = pl->tiles_x;
+  void* args[] = {(void*)&k, (void*)&pl->map[in], (void*)&pout, (void*)&f, (void*)&st, (void*)&res, (void*)&pl->fold_part,
+                  (void*)&pl->mask, (void*)&pl->tile_class, (void*)&list, (void*)&m0, (void*)&nsw, (void*)&force, (void*)&tile_row0, (void*)&order_ntx};
+  return cudaLaunchKernel(pl->kernel, dim3(n, 1), dim3(pl->threads), args, size_t(pl->smem_bytes), stream);
+}
 // Behind all launches of the pass that started at iterate m0 with nsw sweeps.
 static inline cudaError_t tiled_fold_launch(const TiledPlan* pl, const KP& k, unsigned long long* res, int m0, int nsw, cudaStream_t stream) {
   const int lo = std::max(m0, 1), hi = std::min(m0 + std::max(nsw, 1) - 1, k.max_iters);
@@ -1161,3 +1176,4 @@ static inline cudaError_t tiled_fold_launch(const TiledPlan* pl, const KP& k, un
   k_tiled_fold<<<1, 32, 0, stream>>>(pl->fold_part, res, lo, hi);
   return cudaGetLastError();
 }
+#endif  // PM_TILED_DEVICE_ONLY
