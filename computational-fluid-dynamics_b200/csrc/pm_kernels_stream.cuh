@@ -31,7 +31,7 @@
 #ifndef PM_STREAM_MINB
 #define PM_STREAM_MINB 12
 #endif
-static_assert(PM_STREAM_P == 3, "the p ring (P + 1 rows) must divide the 8-tick unroll; the f ring holds the 8 rows in flight and the P + 1 on their way: 12");
+static_assert(PM_STREAM_P == 3, "the rings of rows on their way (P + 1 rows) must divide the 8-tick unroll");
 
 struct StreamGeom {
   int bx0, nbx;  // first strip (tile column of the tiled plan) and number of strips
@@ -41,8 +41,12 @@ struct StreamGeom {
 };
 
 #define PM_STREAM_PRING_BYTES ((PM_STREAM_P + 1) * 1024)
-#define PM_STREAM_FRING_ROWS 12
-#define PM_STREAM_SMEM_BYTES (PM_STREAM_PRING_BYTES + PM_STREAM_FRING_ROWS * 1024)
+// p rows on their way | f rows on their way | f of the 8 rows in flight (slot = tick & 7, like the register slots): every
+// shared-memory address of the loop is the lane's base plus a compile-time constant
+#define PM_STREAM_RING_BYTES (2 * PM_STREAM_PRING_BYTES + 8 * 1024)
+// + the loop counters: the loop body fills the register file of a 12-warp SM, and what ptxas spills to local memory
+// around it comes back from DRAM here (the L1 left beside 12 x 16 KB of shared memory does not hold 12 warps' frames)
+#define PM_STREAM_SMEM_BYTES (PM_STREAM_RING_BYTES + 16)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -51,28 +55,27 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Kernel parameters the ticks read straight from the constant bank (nothing of this is carried in registers).
+struct StreamIO {
+  const double* pin;  // + element offset = the lane's even-column pair of a row; odd pair at + pitch / 2
+  const double* fin;
+  double* pout;
+  int pitch;
+  int rows;           // R: output rows of this chunk
+};
+
 struct StreamCtx {
   double r[8][4];   // rows in flight: slot = tick & 7, cells {E0, O0, E1, O1}
   double acc[8];    // max |r| seen by half-sweep h over the output cells of the chunk
   const double2* pr;  // this lane's 16 bytes in the p ring: row slot s at pr[s * 64], odd columns at + 32
-  const double2* fr;  // likewise in the f ring (12 rows)
-  // f ring: row tau + d sits in slot (tau + d) mod 12; with tau = 8 * pass + U the slot of a static d = U - h (or U + 4 for
-  // the fetch) is fb[class of d] + d, where the class says on which side of the ring's end d falls for this pass
-  // (d in [-7,-5], [-4,-1], [0,3], [4,7], [8,11]); in units of double2 (64 per row)
-  int fb[5];
+  double2* fr;        // likewise in the f ring of rows on their way (P + 1 slots), followed by the f rows in flight (8 slots)
   uint32_t pdst, fdst;  // shared-space addresses of pr / fr for cp.async
-  const double* pin;    // + element offset = the lane's even-column pair of a row; odd pair at + half
-  const double* fin;
-  double* pout;
-  uint32_t gsrc;  // element offset of the next row to fetch (planes stay below 2^32 elements: pm_create checks)
-  uint32_t gdst;  // element offset of the row that leaves in this tick (row tau - 7)
-  int half;      // pitch / 2
-  int pitch;
-  int tau;       // tick (kept by the DYN ticks only)
-  int rows;      // R: output rows of this chunk
-  int nfetch;    // rows still to fetch (kept by the DYN ticks only)
-  unsigned act;  // bit h: the row half-sweep h works on lies in the output rows and this lane holds output columns
-  bool lane_ok;
+  uint32_t gsrc;  // element offset of the next row to fetch, row tau + P + 1 (planes stay below 2^32 elements: stream_supported);
+                  // the row that leaves in tick tau, row tau - 7, is P + 8 rows below it
+  unsigned act;  // bit h: the row half-sweep h works on lies in the output rows
+  // columns 8 .. 119 of the strip: lanes 2 .. 29, read off the lane's ring address (the rings start 1 KiB-aligned) rather than
+  // kept in a predicate across the loop
+  __device__ __forceinline__ bool lane_ok() const { return ((pdst >> 4) & 31u) - 2u < 28u; }
 };
 
 // r = residual with the iterate's own operands; the relaxation is p += cw * r  (rb_half_lean)
@@ -85,21 +88,28 @@ __device__ __forceinline__ double stream_res(const KP& k, double pc, double pw, 
   return res_sum22(k, pc, pw + pe, pn + ps, f);
 }
 
-// m = std::max(m, std::abs(x)) (a NaN never replaces m), branch-free: DSETP.GT with |x| folded in, FSEL |hi|, SEL lo.
+// m = std::max(m, std::abs(x)) (a NaN never replaces m), branch-free; |x| by clearing the sign bit
+// in the integer pipe (abs.f64 became an FP64-pipe DADD -RZ, |x| per call): LOP3 + DSETP.GT + 2 FSEL.
 // (fmax() drags NaN quieting and register copies along; an `if` around two of these turns into branches.)
 __device__ __forceinline__ void stream_max(double& m, double x) {
-  asm("{\n .reg .pred q;\n .reg .f64 a;\n abs.f64 a, %1;\n setp.gt.f64 q, a, %0;\n selp.f64 %0, a, %0, q;\n}" : "+d"(m) : "d"(x));
+  asm("{\n .reg .pred q;\n .reg .b32 lo, hi;\n .reg .f64 a;\n mov.b64 {lo, hi}, %1;\n and.b32 hi, hi, 0x7fffffff;\n mov.b64 a, {lo, hi};\n"
+      " setp.gt.f64 q, a, %0;\n selp.f64 %0, a, %0, q;\n}"
+      : "+d"(m)
+      : "d"(x));
 }
 __device__ __forceinline__ void stream_max_if(double& m, double x, unsigned on) {
-  asm("{\n .reg .pred q, o;\n .reg .f64 a;\n setp.ne.u32 o, %2, 0;\n abs.f64 a, %1;\n setp.gt.and.f64 q, a, %0, o;\n selp.f64 %0, a, %0, q;\n}"
+  asm("{\n .reg .pred q, o;\n .reg .b32 lo, hi;\n .reg .f64 a;\n setp.ne.u32 o, %2, 0;\n mov.b64 {lo, hi}, %1;\n and.b32 hi, hi, 0x7fffffff;\n mov.b64 a, {lo, hi};\n"
+      " setp.gt.and.f64 q, a, %0, o;\n selp.f64 %0, a, %0, q;\n}"
       : "+d"(m)
       : "d"(x), "r"(on));
 }
 
 // DYN: the ticks at the two ends of a chunk, where some half-sweeps work on rows outside the output rows (bit h of c.act);
 // in between every half-sweep's row is an output row, and the lanes that hold halo columns are dropped at the very end.
+// tau0: the tick of U == 0 in this pass of the loop (uniform; only the DYN ticks look at it).
 template <int FORM, int PAR0, int U, bool DYN>
-__device__ __forceinline__ void stream_tick(const KP& k, StreamCtx& c) {
+__device__ __forceinline__ void stream_tick(const KP& k, const StreamIO& io, StreamCtx& c, int tau0) {
+  const int half = io.pitch >> 1;
   constexpr int P = PM_STREAM_P, PR = P + 1;
   constexpr bool tgtE = ((U + PAR0) & 1) == 0;  // this tick's half-sweeps all update the even storage columns (i odd) of their rows
   constexpr int G0 = tgtE ? 0 : 1, G1 = tgtE ? 2 : 3;
@@ -112,26 +122,29 @@ __device__ __forceinline__ void stream_tick(const KP& k, StreamCtx& c) {
     c.r[U][1] = o.x; c.r[U][3] = o.y;
   }
   const double2 nx = c.pr[((U + 1) % PR) * 64 + (tgtE ? 0 : 32)];  // row tau + 1 as it came from HBM: north of half-sweep 0
-  if (DYN) c.act = ((c.act << 1) & 0xffu) | unsigned(unsigned(c.tau - 8) < unsigned(c.rows));
+  // f of row tau moves to its slot among the rows in flight (the lane's own 32 bytes: no synchronisation)
+  const double2 fe = c.fr[(U % PR) * 64], fo = c.fr[(U % PR) * 64 + 32];
+  c.fr[(PR + U) * 64] = fe;
+  c.fr[(PR + U) * 64 + 32] = fo;
+  if (DYN) c.act = ((c.act << 1) & 0xffu) | unsigned(unsigned(tau0 + U - 8) < unsigned(io.rows));
   // the one neighbour per row that lives in another lane: none of these cells changes during this tick
-  double xn[8];
-#pragma unroll
-  for (int h = 0; h < 8; ++h) {
-    constexpr int dummy = 0; (void)dummy;
+  auto outer = [&](int h) {
     const int sl = (U - h) & 7;
-    xn[h] = tgtE ? __shfl_up_sync(0xffffffffu, c.r[sl][3], 1) : __shfl_down_sync(0xffffffffu, c.r[sl][0], 1);
-  }
+    return tgtE ? __shfl_up_sync(0xffffffffu, c.r[sl][3], 1) : __shfl_down_sync(0xffffffffu, c.r[sl][0], 1);
+  };
+  double xq = outer(0);
 #pragma unroll
   for (int h = 0; h < 8; ++h) {
     const int sl = (U - h) & 7, sn = (U - h + 1) & 7, ss = (U - h - 1) & 7;
     const bool jl_odd = ((U - h) & 1) == 0;               // the chunk's first row is odd
     const bool pair_a = tgtE ? jl_odd : !jl_odd;          // (i + jl) even
-    const int d = U - h;
-    const double2 fv = c.fr[c.fb[d <= -5 ? 0 : d <= -1 ? 1 : d <= 3 ? 2 : 3] + d * 64 + (tgtE ? 0 : 32)];
+    const double2 fv = h == 0 ? (tgtE ? fe : fo) : c.fr[(PR + sl) * 64 + (tgtE ? 0 : 32)];
     const double p0 = c.r[sl][G0], p1 = c.r[sl][G1];
+    const double xh = xq;
+    if (h < 7) xq = outer(h + 1);  // one half-sweep ahead
     double w0, e0, w1, e1;
-    if (tgtE) { w0 = xn[h]; e0 = c.r[sl][1]; w1 = c.r[sl][1]; e1 = c.r[sl][3]; }
-    else { w0 = c.r[sl][0]; e0 = c.r[sl][2]; w1 = c.r[sl][2]; e1 = xn[h]; }
+    if (tgtE) { w0 = xh; e0 = c.r[sl][1]; w1 = c.r[sl][1]; e1 = c.r[sl][3]; }
+    else { w0 = c.r[sl][0]; e0 = c.r[sl][2]; w1 = c.r[sl][2]; e1 = xh; }
     const double n0 = h == 0 ? nx.x : c.r[sn][G0], n1 = h == 0 ? nx.y : c.r[sn][G1];
     const double s0 = h == 7 ? cy0 : c.r[ss][G0], s1 = h == 7 ? cy1 : c.r[ss][G1];
     double r0, r1;
@@ -153,38 +166,25 @@ __device__ __forceinline__ void stream_tick(const KP& k, StreamCtx& c) {
     }
   }
   // row tau - 7 has passed all half-sweeps
-  if (c.lane_ok && (!DYN || ((c.act >> 7) & 1u))) {
+  if (c.lane_ok() && (!DYN || ((c.act >> 7) & 1u))) {
     const int so = (U + 1) & 7;
-    *reinterpret_cast<double2*>(c.pout + c.gdst) = make_double2(c.r[so][0], c.r[so][2]);
-    *reinterpret_cast<double2*>(c.pout + c.gdst + c.half) = make_double2(c.r[so][1], c.r[so][3]);
+    const uint32_t gdst = c.gsrc - uint32_t(PR + 7) * uint32_t(io.pitch);
+    *reinterpret_cast<double2*>(io.pout + gdst) = make_double2(c.r[so][0], c.r[so][2]);
+    *reinterpret_cast<double2*>(io.pout + gdst + half) = make_double2(c.r[so][1], c.r[so][3]);
   }
-  c.gdst += uint32_t(c.pitch);
-  // fetch row tau + P + 1 into the slots row tau (p) and row tau - 8 (f) have left
+  // fetch row tau + P + 1 into the slots row tau has left
   {
-    const int d = U + PR;
     const uint32_t pd = c.pdst + uint32_t((U % PR) * 1024);
-    const uint32_t fd = c.fdst + uint32_t((c.fb[d <= 7 ? 3 : 4] + d * 64) * 16);
-    if (!DYN || c.nfetch > 0) {  // nothing beyond the chunk's last row is needed (or may exist)
-      cp_async16(pd, c.pin + c.gsrc);
-      cp_async16(pd + 512u, c.pin + c.gsrc + c.half);
-      cp_async16(fd, c.fin + c.gsrc);
-      cp_async16(fd + 512u, c.fin + c.gsrc + c.half);
+    const uint32_t fd = c.fdst + uint32_t((U % PR) * 1024);
+    if (!DYN || tau0 + U + PR < io.rows + 16) {  // nothing beyond the chunk's last row is needed (or may exist)
+      cp_async16(pd, io.pin + c.gsrc);
+      cp_async16(pd + 512u, io.pin + c.gsrc + half);
+      cp_async16(fd, io.fin + c.gsrc);
+      cp_async16(fd + 512u, io.fin + c.gsrc + half);
     }
     cp_async_commit();
-    c.gsrc += uint32_t(c.pitch);
-    if (DYN) --c.nfetch;
+    c.gsrc += uint32_t(io.pitch);
   }
-  if (DYN) ++c.tau;
-}
-
-// Offsets of the five classes of d for the pass whose first tick sits in ring slot `base` (0, 8, 4, 0, ...).
-__device__ __forceinline__ void stream_fring_bases(StreamCtx& c, int base) {
-  constexpr int N = PM_STREAM_FRING_ROWS;
-  c.fb[0] = (base + (base <= 4 ? N : 0)) * 64;   // d in [-7,-5]: below slot 0 unless the pass starts at 8
-  c.fb[1] = (base + (base == 0 ? N : 0)) * 64;   // d in [-4,-1]
-  c.fb[2] = base * 64;                           // d in [0,3]
-  c.fb[3] = (base - (base == 8 ? N : 0)) * 64;   // d in [4,7]
-  c.fb[4] = (base - (base >= 4 ? N : 0)) * 64;   // d in [8,11]
 }
 
 template <int FORM, int PAR0>
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(32, PM_STREAM_MINB)
   constexpr int T = 4, H = 2 * T, P = PM_STREAM_P, PR = P + 1;
   using C = TileCfg<PM_PPE_SOR_RB, T>;
   static_assert(C::H == H && C::SW == 128, "strips are the tile columns of the tiled plan");
-  extern __shared__ __align__(16) unsigned char stream_smem[];
+  extern __shared__ __align__(1024) unsigned char stream_smem[];
   const int lane = threadIdx.x;
   StopWords<T> stopw;
   if (!force) stopw = stop_words_load<T>(st, res_bits, m0);
@@ -214,34 +214,24 @@ __global__ void __launch_bounds__(32, PM_STREAM_MINB)
     c.acc[s] = 0.0;
   }
   c.pr = reinterpret_cast<const double2*>(stream_smem) + lane;
-  c.fr = reinterpret_cast<const double2*>(stream_smem + PM_STREAM_PRING_BYTES) + lane;
-  stream_fring_bases(c, 0);
+  c.fr = reinterpret_cast<double2*>(stream_smem + PM_STREAM_PRING_BYTES) + lane;
   c.pdst = smem_u32(c.pr);
   c.fdst = smem_u32(c.fr);
-  c.pin = pin;
-  c.fin = fsplit;
-  c.pout = pout;
-  c.pitch = k.pitch;
-  c.half = k.pitch >> 1;
+  const StreamIO io{pin, fsplit, pout, k.pitch, yb - ya};
+  const int half = k.pitch >> 1;
   c.gsrc = uint32_t(k.padr + jstart) * uint32_t(k.pitch) + uint32_t(pe);
-  c.gdst = uint32_t(k.padr + jstart - 7) * uint32_t(k.pitch) + uint32_t(pe);
-  c.tau = 0;
-  c.rows = yb - ya;
   c.act = 0u;
-  c.lane_ok = lane >= 2 && lane <= 29;  // columns 8 .. 119 of the strip
-  const int nrows = c.rows + 2 * H;      // rows that enter: the output rows and H below / above
-  c.nfetch = nrows;
+  static_assert(H == 8, "rows + 16 rows enter: the output rows and H below / above");
   // rows 0 .. P
 #pragma unroll
   for (int q = 0; q < PR; ++q) {
     const uint32_t pd = c.pdst + uint32_t(q * 1024), fd = c.fdst + uint32_t(q * 1024);
-    cp_async16(pd, c.pin + c.gsrc);
-    cp_async16(pd + 512u, c.pin + c.gsrc + c.half);
-    cp_async16(fd, c.fin + c.gsrc);
-    cp_async16(fd + 512u, c.fin + c.gsrc + c.half);
+    cp_async16(pd, io.pin + c.gsrc);
+    cp_async16(pd + 512u, io.pin + c.gsrc + half);
+    cp_async16(fd, io.fin + c.gsrc);
+    cp_async16(fd + 512u, io.fin + c.gsrc + half);
     cp_async_commit();
-    c.gsrc += uint32_t(c.pitch);
-    --c.nfetch;
+    c.gsrc += uint32_t(io.pitch);
   }
   if (!force) {  // the reference's loop test (uniform over the grid), as in k_ppe_tiled
     int first;
@@ -256,37 +246,41 @@ __global__ void __launch_bounds__(32, PM_STREAM_MINB)
   }
   // Tick tau needs rows tau and tau + 1; the last output row leaves at tick rows + 14.  Eight ticks per pass of the loop;
   // passes 2 .. rows / 8 (ticks 16 .. rows + 7) have every half-sweep on an output row and every fetch inside the chunk.
-  const int nticks = c.rows + 2 * H - 1;
-  const int nit = (nticks + 7) >> 3, it_steady_last = min(c.rows >> 3, nit - 1);
-  int fbase = 0;
+  volatile int* loopc = reinterpret_cast<volatile int*>(stream_smem + PM_STREAM_RING_BYTES);
+  {
+    const int nticks = io.rows + 2 * H - 1;
+    const int nit0 = (nticks + 7) >> 3;
+    loopc[0] = 0;                             // pass of the loop (every lane writes the same words)
+    loopc[1] = nit0;                          // passes
+    loopc[2] = min(io.rows >> 3, nit0 - 1);   // last steady one
+  }
 #pragma unroll 1
-  for (int it = 0; it < nit; ++it) {
+  for (;;) {
+    const int it = loopc[0], nit = loopc[1], it_steady_last = loopc[2];
+    if (it >= nit) break;
+    loopc[0] = it + 1;
     if (it >= 2 && it <= it_steady_last) {
-      stream_tick<FORM, PAR0, 0, false>(k, c);
-      stream_tick<FORM, PAR0, 1, false>(k, c);
-      stream_tick<FORM, PAR0, 2, false>(k, c);
-      stream_tick<FORM, PAR0, 3, false>(k, c);
-      stream_tick<FORM, PAR0, 4, false>(k, c);
-      stream_tick<FORM, PAR0, 5, false>(k, c);
-      stream_tick<FORM, PAR0, 6, false>(k, c);
-      stream_tick<FORM, PAR0, 7, false>(k, c);
+      stream_tick<FORM, PAR0, 0, false>(k, io, c, 0);
+      stream_tick<FORM, PAR0, 1, false>(k, io, c, 0);
+      stream_tick<FORM, PAR0, 2, false>(k, io, c, 0);
+      stream_tick<FORM, PAR0, 3, false>(k, io, c, 0);
+      stream_tick<FORM, PAR0, 4, false>(k, io, c, 0);
+      stream_tick<FORM, PAR0, 5, false>(k, io, c, 0);
+      stream_tick<FORM, PAR0, 6, false>(k, io, c, 0);
+      stream_tick<FORM, PAR0, 7, false>(k, io, c, 0);
     } else {
-      if (it_steady_last >= 2 && it == it_steady_last + 1) {  // the steady passes do not keep the bits (all were set) nor the counters
+      if (it_steady_last >= 2 && it == it_steady_last + 1) {  // the steady passes do not keep the bits: all were set
         c.act = 0xffu;
-        c.tau += 8 * (it_steady_last - 1);
-        c.nfetch -= 8 * (it_steady_last - 1);
       }
-      stream_tick<FORM, PAR0, 0, true>(k, c);
-      stream_tick<FORM, PAR0, 1, true>(k, c);
-      stream_tick<FORM, PAR0, 2, true>(k, c);
-      stream_tick<FORM, PAR0, 3, true>(k, c);
-      stream_tick<FORM, PAR0, 4, true>(k, c);
-      stream_tick<FORM, PAR0, 5, true>(k, c);
-      stream_tick<FORM, PAR0, 6, true>(k, c);
-      stream_tick<FORM, PAR0, 7, true>(k, c);
+      stream_tick<FORM, PAR0, 0, true>(k, io, c, 8 * it);
+      stream_tick<FORM, PAR0, 1, true>(k, io, c, 8 * it);
+      stream_tick<FORM, PAR0, 2, true>(k, io, c, 8 * it);
+      stream_tick<FORM, PAR0, 3, true>(k, io, c, 8 * it);
+      stream_tick<FORM, PAR0, 4, true>(k, io, c, 8 * it);
+      stream_tick<FORM, PAR0, 5, true>(k, io, c, 8 * it);
+      stream_tick<FORM, PAR0, 6, true>(k, io, c, 8 * it);
+      stream_tick<FORM, PAR0, 7, true>(k, io, c, 8 * it);
     }
-    fbase = fbase >= 4 ? fbase - 4 : fbase + 8;  // (fbase + 8) mod 12
-    stream_fring_bases(c, fbase);
   }
   cp_async_wait<0>();
   // per-iterate maxima: entry t = colour-0 part of iterate m0 + t (half-sweep 2t, operands before the update) and the
@@ -299,7 +293,7 @@ __global__ void __launch_bounds__(32, PM_STREAM_MINB)
       const double m = sc * c.acc[2 * t - 1];
       if (m > v) v = m;
     }
-    v = warp_max_nonneg(c.lane_ok ? v : 0.0);  // the lanes of the strip's halo columns hold no output cell
+    v = warp_max_nonneg(c.lane_ok() ? v : 0.0);  // the lanes of the strip's halo columns hold no output cell
     const int m = m0 + t;
     const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
     if (lane == 0 && bits != 0ull && m >= 1 && m <= k.max_iters)
@@ -415,7 +409,7 @@ static inline cudaError_t stream_launch(const StreamPlan* sp, const TiledPlan* p
   const double* pin = pl->p[in];
   double* pout = pl->p[in ^ 1];
   void* args[] = {(void*)&k, (void*)&pin, (void*)&pout, (void*)&fsplit, (void*)&st, (void*)&res, (void*)&pl->fold_part, (void*)&sp->g, (void*)&m0, (void*)&force};
-  static_assert(PM_STREAM_SMEM_BYTES == 16 * 1024, "12 warps per SM");
+  static_assert(12 * (PM_STREAM_SMEM_BYTES + 1024) <= 227 * 1024, "12 warps per SM");
   return cudaLaunchKernel(sp->kernel, dim3(sp->items), dim3(32), args, PM_STREAM_SMEM_BYTES, stream);
 }
 #endif  // PM_TILED_DEVICE_ONLY
