@@ -426,6 +426,62 @@ def test_large_grid_8192_tiled_equals_general_path(pm, exact):
     assert np.isfinite(out[0][1]).all() and np.abs(out[0][1]).max() > 0
 
 
+def _stream_pair(pm, monkeypatch, cfg, seed, steps=1, prepare=None):
+    """The same production red-black problem with the streaming pass (default) and with the tiled kernel alone."""
+    out = []
+    for no_stream in (True, False):
+        if no_stream:
+            monkeypatch.setenv("PM_NO_STREAM", "1")
+        else:
+            monkeypatch.delenv("PM_NO_STREAM", raising=False)
+        S = pm.Solver(cfg)
+        S.fill_random(seed)
+        if cfg.case_id != 0:
+            S.apply_bc(0)
+        if prepare:
+            prepare(S)
+        r = S.step(steps)
+        out.append((r, [S.download(f) for f in range(6)], S.timing().kernel_launches))
+        S.close()
+    return out
+
+
+@pytest.mark.parametrize("case_id,nx,ny,K,steps", [(0, 1024, 1024, 23, 2), (0, 2000, 1500, 40, 1), (1, 2048, 1024, 24, 2), (1, 1500, 700, 9, 1), (0, 1400, 420, 100, 1)])
+def test_streaming_pass_is_bit_identical_to_the_tiled_kernel(pm, monkeypatch, case_id, nx, ny, K, steps):
+    """k_ppe_stream (interior tiles of production red-black solves, pm_kernels_stream.cuh) against k_ppe_tiled over the whole
+    grid: every field, the iteration count and the residual, bit for bit -- also where K is not a multiple of the four
+    sweeps of a pass (the last pass and the residual-only pass run on the tiled kernel alone)."""
+    if os.environ.get("PM_LIB", "").endswith("cs4.so"):
+        pytest.skip("the cluster build does not stream")
+    cfg = make_cfg(pm, case_id, nx, ny, RB, 0, K, path=2)
+    cfg.tol_factor = 1e-13  # large cavities: keep the reference's loop-entry rule (1.0 > tolerance) from skipping the solve
+    (ra, fa, la), (rb, fb, lb) = _stream_pair(pm, monkeypatch, cfg, 31, steps)
+    assert lb > la, "the streaming pass did not run (two launches per full pass instead of one)"
+    assert (ra.iterations, ra.residual) == (rb.iterations, rb.residual) and ra.iterations == K
+    for fid, (a, b) in enumerate(zip(fa, fb)):
+        assert np.isfinite(b).all()
+        assert bits_equal(a, b), f"field {fid}: max abs {np.abs(a - b).max():.3e}"
+
+
+def test_streaming_pass_stops_on_the_same_iterate(pm, monkeypatch):
+    """A solve that meets its tolerance in the middle of a pass: loop test on the device, replay of the partial pass."""
+    if os.environ.get("PM_LIB", "").endswith("cs4.so"):
+        pytest.skip("the cluster build does not stream")
+    cfg = make_cfg(pm, 1, 1300, 420, RB, 0, 57, path=2)
+    S = pm.Solver(cfg)
+    S.fill_random(8); S.apply_bc(0)
+    r0 = S.step(1)
+    S.close()
+    assert r0.iterations == 57
+    cfg.max_iters = 10000
+    cfg.tol_factor, cfg.abs_tol = 0.0, r0.residual * (1.0 + 1e-9)
+    (ra, fa, _), (rb, fb, _) = _stream_pair(pm, monkeypatch, cfg, 8)
+    assert 1 <= rb.iterations <= 57 and not rb.hit_cap
+    assert (ra.iterations, ra.residual) == (rb.iterations, rb.residual)
+    for a, b in zip(fa, fb):
+        assert bits_equal(a, b)
+
+
 @pytest.mark.parametrize("name", ["cavity_default", "channel_default", "step_default", "cavity_k50_32", "channel_k50", "step_k50",
                                   "cavity_cfg0", "channel_cfg1"])
 def test_sor_lex_reproduces_the_reference_bit_for_bit(pm, name):
