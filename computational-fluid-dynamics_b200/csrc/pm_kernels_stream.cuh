@@ -126,6 +126,20 @@ __device__ __forceinline__ void stream_tick(const KP& k, const StreamIO& io, Str
   const double2 fe = c.fr[(U % PR) * 64], fo = c.fr[(U % PR) * 64 + 32];
   c.fr[(PR + U) * 64] = fe;
   c.fr[(PR + U) * 64 + 32] = fo;
+  // Fetch row tau + P + 1 into the slots row tau has just been read from -- right away, not at the end of the tick: the
+  // load/store unit takes the reads above and these copies in order, and the row gains a tick to arrive in.
+  {
+    const uint32_t pd = c.pdst + uint32_t((U % PR) * 1024);
+    const uint32_t fd = c.fdst + uint32_t((U % PR) * 1024);
+    if (!DYN || tau0 + U + PR < io.rows + 16) {  // nothing beyond the chunk's last row is needed (or may exist)
+      cp_async16(pd, io.pin + c.gsrc);
+      cp_async16(pd + 512u, io.pin + c.gsrc + half);
+      cp_async16(fd, io.fin + c.gsrc);
+      cp_async16(fd + 512u, io.fin + c.gsrc + half);
+    }
+    cp_async_commit();
+    c.gsrc += uint32_t(io.pitch);
+  }
   if (DYN) c.act = ((c.act << 1) & 0xffu) | unsigned(unsigned(tau0 + U - 8) < unsigned(io.rows));
   // the one neighbour per row that lives in another lane: none of these cells changes during this tick
   auto outer = [&](int h) {
@@ -168,22 +182,9 @@ __device__ __forceinline__ void stream_tick(const KP& k, const StreamIO& io, Str
   // row tau - 7 has passed all half-sweeps
   if (c.lane_ok() && (!DYN || ((c.act >> 7) & 1u))) {
     const int so = (U + 1) & 7;
-    const uint32_t gdst = c.gsrc - uint32_t(PR + 7) * uint32_t(io.pitch);
+    const uint32_t gdst = c.gsrc - uint32_t(PR + 8) * uint32_t(io.pitch);  // gsrc already points at row tau + P + 2
     *reinterpret_cast<double2*>(io.pout + gdst) = make_double2(c.r[so][0], c.r[so][2]);
     *reinterpret_cast<double2*>(io.pout + gdst + half) = make_double2(c.r[so][1], c.r[so][3]);
-  }
-  // fetch row tau + P + 1 into the slots row tau has left
-  {
-    const uint32_t pd = c.pdst + uint32_t((U % PR) * 1024);
-    const uint32_t fd = c.fdst + uint32_t((U % PR) * 1024);
-    if (!DYN || tau0 + U + PR < io.rows + 16) {  // nothing beyond the chunk's last row is needed (or may exist)
-      cp_async16(pd, io.pin + c.gsrc);
-      cp_async16(pd + 512u, io.pin + c.gsrc + half);
-      cp_async16(fd, io.fin + c.gsrc);
-      cp_async16(fd + 512u, io.fin + c.gsrc + half);
-    }
-    cp_async_commit();
-    c.gsrc += uint32_t(io.pitch);
   }
 }
 
