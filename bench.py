@@ -269,6 +269,23 @@ def small_configs(pm, local, with_cpu):
         S.close()
         row = {"config": name, "gpu_ms_per_step": 1e3 * dt / steps, "gpu_iterations_per_step": iters / steps,
                "gpu_us_per_iteration": 1e6 * dt / max(iters, 1), "ordering": "red-black (production); the reference's is lexicographic"}
+        # beyond the reference (non-default, `--omega mixed` of the drivers): the relaxation factor of the mixed-BC operator
+        cfg2 = pm.config_init(cid, *a)
+        cfg2.ppe_method, cfg2.device = pm.PPE_SOR_RB, local
+        cfg2.omega = pm.lib().pm_omega_mixed_bc(cid, cfg2.nx, cfg2.ny, cfg2.dx, cfg2.dy)
+        S = pm.Solver(cfg2)
+        S.apply_bc(0)
+        S.step(2)
+        S.sync()
+        t0 = time.perf_counter()
+        iters2 = 0
+        for _ in range(steps):
+            iters2 += S.step(1).iterations
+        S.sync()
+        dt2 = time.perf_counter() - t0
+        S.close()
+        row["omega_mixed"] = {"omega": cfg2.omega, "reference_omega": cfg.omega, "gpu_ms_per_step": 1e3 * dt2 / steps,
+                              "gpu_iterations_per_step": iters2 / steps, "what": "same solver, same tolerance, omega = pm_omega_mixed_bc (include/pm.h)"}
         if with_cpu:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import orc

@@ -52,6 +52,7 @@ struct Options {
   int steps = -1;
   double tfinal = -1.0;
   int ppe = PM_PPE_SOR_RB;
+  std::string omega = "";  // "" = the reference's factor; "mixed" = pm_omega_mixed_bc; or a number
   int max_iters = -1;
   int exact = 0;
   int path = PM_PATH_AUTO;
@@ -67,7 +68,7 @@ struct Options {
 [[noreturn]] void usage(const char* prog) {
   std::fprintf(stderr,
                "usage: %s [--Re R] [--Nx N] [--Ny N] [--dt T]\n"
-               "          [--steps N | --tfinal T] [--ppe sor-rb|jacobi|sor-lex] [--max-iters K] [--exact 0|1]\n"
+               "          [--steps N | --tfinal T] [--ppe sor-rb|jacobi|sor-lex|cheby] [--omega reference|mixed|W] [--max-iters K] [--exact 0|1]\n"
                "          [--path auto|simple|tiled] [--sweeps T] [--print-interval N] [--save-interval N]\n"
                "          [--no-vtk] [--outdir DIR] [--device D] [--gpus N] [--stop-after N]\n"
                "Omitted flags keep the reference's compiled-in constants.\n",
@@ -99,11 +100,13 @@ Options parse(int argc, char** argv) {
     else if (f == "--stop-after") o.stop_after = std::atoi(val());
     else if (f == "--outdir") o.outdir = val();
     else if (f == "--no-vtk") o.vtk = false;
+    else if (f == "--omega") o.omega = val();
     else if (f == "--ppe") {
       const std::string v = val();
       if (v == "sor-rb") o.ppe = PM_PPE_SOR_RB;
       else if (v == "jacobi") o.ppe = PM_PPE_JACOBI;
       else if (v == "sor-lex") o.ppe = PM_PPE_SOR_LEX;
+      else if (v == "cheby" || v == "sor-cheby") o.ppe = PM_PPE_SOR_CHEBY;
       else usage(argv[0]);
     } else if (f == "--path") {
       const std::string v = val();
@@ -396,6 +399,10 @@ int main(int argc, char** argv) {
     c.sweeps_per_pass = o.sweeps;
     c.device = o.device;
     if (o.ppe == PM_PPE_JACOBI) c.omega = 1.0;  // plain Jacobi diverges for omega > 1; the verification mode runs unrelaxed
+    // beyond the reference: a factor derived from the operator's own boundary conditions (include/pm.h)
+    if (o.omega == "mixed" || (o.omega.empty() && o.ppe == PM_PPE_SOR_CHEBY)) c.omega = pm_omega_mixed_bc(c.case_id, c.nx, c.ny, c.dx, c.dy);
+    else if (o.omega != "" && o.omega != "reference") c.omega = std::atof(o.omega.c_str());
+    if (!(c.omega > 0.0 && c.omega < 2.0)) throw std::runtime_error("--omega must lie in (0, 2)");
     if (o.max_iters >= 0) c.max_iters = o.max_iters;
     if (o.tfinal > 0) { c.final_time = o.tfinal; c.total_steps = static_cast<int>(c.final_time / c.dt); }
     run.total_steps = o.steps >= 0 ? o.steps : c.total_steps;

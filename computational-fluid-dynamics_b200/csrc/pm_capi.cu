@@ -72,6 +72,8 @@ struct pm_solver {
   bool use_small = false;  // persistent single-CTA solve (small grids)
   bool no_cluster = false; // PM_NO_CLUSTER=1 in the environment: keep the persistent solve on one SM
   int sweeps = 1;
+  int cheby_q = 0;       // PM_PPE_SOR_CHEBY: colour half-sweeps launched in this solve, and the factor of the last one
+  double cheby_w = 1.0;
   TiledPlan tiled{};
   // streaming pass (pm_kernels_stream.cuh) over the interior tiles of the plan; f in the split-row layout for it
   StreamPlan splan{};
@@ -170,6 +172,14 @@ extern "C" int pm_nccl_unique_id(uint8_t out[128]) {
 // ---------------------------------------------------------------------------
 // create / destroy
 // ---------------------------------------------------------------------------
+// Everything in KP that depends on the relaxation factor (PM_PPE_SOR_CHEBY changes it with every colour half-sweep).
+static void kp_set_omega(KP& k, double omega) {
+  k.omega = omega; k.om1 = 1.0 - omega;
+  for (int n = 1; n <= 4; ++n) k.wnc[n] = omega / n;
+  k.wnc[0] = 0.0;
+  k.cw = k.case_id == PM_CASE_CAVITY ? omega * k.hh / 4.0 : omega / k.denom;
+}
+
 static void fill_kp(pm_solver* s, int j0, int nyl) {
   const pm_config& c = s->cfg;
   KP& k = s->kp;
@@ -188,12 +198,9 @@ static void fill_kp(pm_solver* s, int j0, int nyl) {
   k.idx2 = 1.0 / (c.dx * c.dx); k.idy2 = 1.0 / (c.dy * c.dy);
   k.hh = c.dx * c.dx;
   k.nu = c.nu; k.dt = c.dt; k.uref = c.u_ref; k.two_uref = 2.0 * c.u_ref;
-  k.omega = c.omega; k.om1 = 1.0 - c.omega;
-  for (int n = 1; n <= 4; ++n) k.wnc[n] = c.omega / n;
-  k.wnc[0] = 0.0;
   k.denom = 2.0 * (k.idx2 + k.idy2);
   k.rdenom = 1.0 / k.denom;
-  k.cw = c.case_id == PM_CASE_CAVITY ? c.omega * k.hh / 4.0 : c.omega / k.denom;
+  kp_set_omega(k, c.omega);
   if (c.case_id == PM_CASE_CAVITY) {
     const double dti = 1.0 / c.dt;
     k.src_coef = dti * c.rho;               // time_step_inv * density, cavity-01.cpp:624
@@ -336,7 +343,7 @@ static int create_impl(pm_solver* s, const pm_config* cfg) {
   if (c.kernel_path == PM_PATH_TILED && !tiled_ok)
     return fail(s, PM_ERR_UNSUPPORTED, "tiled path: jacobi / sor-rb (with the obstacle mask: sor-rb only)");
   const size_t pbytes = size_t(c.ny + 2) * size_t(c.nx + 2) * sizeof(double);
-  const bool small_ok = c.nranks == 1 && c.ppe_method != PM_PPE_SOR_LEX && pbytes <= size_t(200) * 1024 &&
+  const bool small_ok = c.nranks == 1 && c.ppe_method != PM_PPE_SOR_LEX && c.ppe_method != PM_PPE_SOR_CHEBY && pbytes <= size_t(200) * 1024 &&
                         size_t(c.nx) * size_t(c.ny) <= size_t(20) * 1024;
   if (c.kernel_path == PM_PATH_PERSISTENT && !small_ok)
     return fail(s, PM_ERR_UNSUPPORTED, "persistent path needs a single rank and a pressure field that fits shared memory");
@@ -391,7 +398,7 @@ extern "C" int pm_create(const pm_config* cfg, pm_solver** out) {
   // create_field, cavity-01.cpp:57-59
   if (cfg->nx <= 0 || cfg->ny <= 0) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "Field dimensions must be positive");
   if (cfg->case_id < PM_CASE_CAVITY || cfg->case_id > PM_CASE_STEP) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "unknown case %d", cfg->case_id);
-  if (cfg->ppe_method < PM_PPE_JACOBI || cfg->ppe_method > PM_PPE_SOR_LEX) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "unknown ppe method %d", cfg->ppe_method);
+  if (cfg->ppe_method < PM_PPE_JACOBI || cfg->ppe_method > PM_PPE_SOR_CHEBY) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "unknown ppe method %d", cfg->ppe_method);
   if (cfg->nx < 2 || cfg->ny < 2) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "grid must be at least 2x2");
   if (cfg->kernel_path < PM_PATH_AUTO || cfg->kernel_path > PM_PATH_PERSISTENT) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "unknown kernel path %d", cfg->kernel_path);
   if (cfg->sweeps_per_pass < 0 || cfg->sweeps_per_pass > 4) return fail(nullptr, PM_ERR_INVALID_ARGUMENT, "sweeps_per_pass out of range");
@@ -826,10 +833,21 @@ static int launch_iteration_simple(pm_solver* s, int krel, int kabs) {
     PMTRY(allreduce_res(s, kabs, 1));
   } else {
     double* p = s->pl[s->p_cur];
-    k_rb_colour<A, FORM><<<half_grid(k), cell_block(), 0, s->stream>>>(k, p, f, s->mask, s->d_state, s->d_res, krel, 0, 1, fuse);
+    KP k0 = k, k1 = k;  // per colour half-sweep: the relaxation factor of PM_PPE_SOR_CHEBY moves (include/pm.h)
+    if (method == PM_PPE_SOR_CHEBY) {
+      if (kabs == 1) { s->cheby_q = 0; s->cheby_w = 1.0; }
+      if (s->cheby_q != 2 * (kabs - 1)) return fail(s, PM_ERR_RUNTIME, "sor-cheby: iterations must be launched in order");
+      const double rho2 = pmi_cheby_rho2(s->cfg.omega);
+      if (s->cheby_q > 0) s->cheby_w = pmi_cheby_next_omega(rho2, s->cheby_q, s->cheby_w);
+      kp_set_omega(k0, s->cheby_w);
+      s->cheby_w = pmi_cheby_next_omega(rho2, s->cheby_q + 1, s->cheby_w);
+      kp_set_omega(k1, s->cheby_w);
+      s->cheby_q += 2;
+    }
+    k_rb_colour<A, FORM><<<half_grid(k), cell_block(), 0, s->stream>>>(k0, p, f, s->mask, s->d_state, s->d_res, krel, 0, 1, fuse);
     CKL(s);
     PMTRY(exchange_halo1(s, p));
-    k_rb_colour<A, FORM><<<half_grid(k), cell_block(), 0, s->stream>>>(k, p, f, s->mask, s->d_state, s->d_res, krel, 1, 0, fuse);
+    k_rb_colour<A, FORM><<<half_grid(k), cell_block(), 0, s->stream>>>(k1, p, f, s->mask, s->d_state, s->d_res, krel, 1, 0, fuse);
     CKL(s);
     if (masked) {
       k_pghost_walls<<<(std::max(k.nx, k.nyl) + 255) / 256, 256, 0, s->stream>>>(k, p, s->d_state, s->d_res, krel, 0, 1);

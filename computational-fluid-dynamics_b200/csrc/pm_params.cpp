@@ -106,3 +106,22 @@ extern "C" int pm_slab_range(int ny, int nranks, int rank, int* j0, int* ny_loca
   if (ny_local) *ny_local = mine;
   return PM_OK;
 }
+
+extern "C" double pm_cheby_omega(double omega, int q) {
+  const double rho2 = pmi_cheby_rho2(omega);
+  double w = 1.0;
+  for (int n = 1; n <= q; ++n) w = pmi_cheby_next_omega(rho2, n, w);
+  return w;
+}
+
+extern "C" double pm_omega_mixed_bc(int case_id, int nx, int ny, double dx, double dy) {
+  const double pi = 3.14159265358979323846;
+  double rho;
+  if (case_id == PM_CASE_CAVITY) {
+    rho = 0.5 * (1.0 + std::cos(pi / (2.0 * ny + 1.0)));
+  } else {
+    const double ix2 = 1.0 / (dx * dx), iy2 = 1.0 / (dy * dy);
+    rho = (ix2 * std::cos(pi / (2.0 * nx + 1.0)) + iy2) / (ix2 + iy2);
+  }
+  return 2.0 / (1.0 + std::sqrt(std::max(1e-14, 1.0 - rho * rho)));
+}

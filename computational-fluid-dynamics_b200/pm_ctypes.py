@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("PM_LIB") or os.path.join(HERE, "lib", "libpm.so")  # 
 
 PM_OK = 0
 CASE_CAVITY, CASE_CHANNEL, CASE_STEP = 0, 1, 2
-PPE_JACOBI, PPE_SOR_RB, PPE_SOR_LEX = 0, 1, 2
+PPE_JACOBI, PPE_SOR_RB, PPE_SOR_LEX, PPE_SOR_CHEBY = 0, 1, 2, 3
 F_U, F_V, F_P, F_USTAR, F_VSTAR, F_F = range(6)
 PATH_AUTO, PATH_SIMPLE, PATH_TILED, PATH_PERSISTENT = 0, 1, 2, 3
 
@@ -59,7 +59,7 @@ def field_shape(field, nx, ny):
 
 
 EXPORTS = [
-    "pm_config_init", "pm_slab_range", "pm_create", "pm_destroy", "pm_last_error", "pm_status_string",
+    "pm_config_init", "pm_slab_range", "pm_cheby_omega", "pm_omega_mixed_bc", "pm_create", "pm_destroy", "pm_last_error", "pm_status_string",
     "pm_abi_version", "pm_nccl_unique_id", "pm_upload", "pm_download", "pm_slab_rows", "pm_upload_slab", "pm_download_slab", "pm_upload_mask", "pm_download_mask",
     "pm_fill_random", "pm_fill_random_scaled", "pm_fill_zero", "pm_apply_bc", "pm_predict", "pm_source", "pm_ppe_solve", "pm_correct",
     "pm_step", "pm_host_step_submit", "pm_host_step_run", "pm_host_step_drain", "pm_diagnostics", "pm_sync", "pm_get_timing", "pm_timer_start", "pm_timer_stop",
@@ -81,6 +81,8 @@ def lib():
     vp, dp = C.c_void_p, C.POINTER(C.c_double)
     L.pm_config_init.argtypes = [C.POINTER(PmConfig), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
     L.pm_slab_range.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.pm_cheby_omega.argtypes = [C.c_double, C.c_int]; L.pm_cheby_omega.restype = C.c_double
+    L.pm_omega_mixed_bc.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]; L.pm_omega_mixed_bc.restype = C.c_double
     L.pm_create.argtypes = [C.POINTER(PmConfig), C.POINTER(vp)]
     L.pm_destroy.argtypes = [vp]
     L.pm_last_error.argtypes = [vp]; L.pm_last_error.restype = C.c_char_p

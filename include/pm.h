@@ -55,8 +55,25 @@ typedef enum pm_case {
 typedef enum pm_ppe_method {
   PM_PPE_JACOBI = 0,  /* deterministic verification mode */
   PM_PPE_SOR_RB = 1,  /* production: red-black SOR        */
-  PM_PPE_SOR_LEX = 2  /* reference ordering, wavefront-parallel, single rank only */
+  PM_PPE_SOR_LEX = 2, /* reference ordering, wavefront-parallel, single rank only */
+  /* Red-black SOR with Chebyshev acceleration (the README's "better Poisson solver" item, README.md:39; not in the
+   * reference code): the relaxation factor changes with every colour half-sweep q = 0, 1, 2, ...
+   *   w_0 = 1,  w_1 = 1 / (1 - rho^2 / 2),  w_q = 1 / (1 - rho^2 w_{q-1} / 4),   rho^2 = 1 - (2 / omega - 1)^2
+   * (rho = the Jacobi spectral radius pm_config.omega was derived from, cavity-01.cpp:74-78), and tends to omega.  The
+   * error norm then falls from the first sweep on instead of growing first, as it does with omega from the start.
+   * Same sweeps, ghosts, residual and loop test as PM_PPE_SOR_RB; general kernel path; shards over slabs. */
+  PM_PPE_SOR_CHEBY = 3
 } pm_ppe_method;
+
+/* w_q of PM_PPE_SOR_CHEBY from w_{q-1} (q >= 1; w_0 = 1).  Inline helpers (not exports) so that the library and the CPU
+ * oracle evaluate one expression tree. */
+static inline double pmi_cheby_next_omega(double rho2, int q, double w_prev) {
+  return q == 1 ? 1.0 / (1.0 - 0.5 * rho2) : 1.0 / (1.0 - 0.25 * rho2 * w_prev);
+}
+static inline double pmi_cheby_rho2(double omega) {
+  const double t = 2.0 / omega - 1.0;
+  return 1.0 - t * t;
+}
 
 typedef enum pm_field {
   PM_FIELD_U = 0,      /* u_corrected */
@@ -126,6 +143,22 @@ int pm_config_init(pm_config* cfg, int case_id, int nx, int ny, double re, doubl
 
 /* Rows of the global grid owned by `rank`: interior rows j0+1 .. j0+ny_local. */
 int pm_slab_range(int ny, int nranks, int rank, int* j0, int* ny_local);
+
+/* Relaxation factor of colour half-sweep q (0, 1, 2, ...) of PM_PPE_SOR_CHEBY for a problem whose fixed-omega solver would
+ * use `omega` (host-only, no device needed). */
+double pm_cheby_omega(double omega, int q);
+
+/* A relaxation factor derived from the operator the solvers actually iterate on.  The reference takes omega from the
+ * Jacobi spectral radius of the DIRICHLET problem (cavity-01.cpp:74-78, channel-01.cpp:76-81), but its pressure problem is
+ * Neumann on all walls but one (cavity: the south ghost row is held at 0; channel / step: the outlet ghost column), whose
+ * slowest Jacobi mode is constant along the all-Neumann direction and a quarter wave along the other:
+ *   cavity:   rho = (1 + cos(pi / (2 ny + 1))) / 2
+ *   channel:  rho = (cos(pi / (2 nx + 1)) / dx^2 + 1 / dy^2) / (1 / dx^2 + 1 / dy^2)        (step: the same)
+ *   omega = 2 / (1 + sqrt(1 - rho^2)).
+ * With it red-black SOR needs 3-4.4 x fewer iterations on the reference's own configurations (tests/test_oracle.py), and the
+ * channel and step cases converge inside the reference's cap of 10000, which they never do with the reference's factor.
+ * Not the default: the drivers take it with `--omega mixed` (and with `--ppe cheby`, whose schedule then tends to it). */
+double pm_omega_mixed_bc(int case_id, int nx, int ny, double dx, double dy);
 
 /* ---- lifetime ---------------------------------------------------------- */
 int pm_create(const pm_config* cfg, pm_solver** out);

@@ -320,6 +320,7 @@ void ppe(Oracle& o, pm_ppe_result* out) {
   }
   Arr tmp;
   if (o.c.ppe_method == PM_PPE_JACOBI) tmp = o.p;
+  double cheby_w = 1.0;
   int it = 0;
   while (res > tol && it < o.c.max_iters) {
     ++it;
@@ -328,6 +329,18 @@ void ppe(Oracle& o, pm_ppe_result* out) {
     } else if (o.c.ppe_method == PM_PPE_SOR_RB) {
       sweep_inplace_rows(o, o.p, 0, 1, ny);
       sweep_inplace_rows(o, o.p, 1, 1, ny);
+    } else if (o.c.ppe_method == PM_PPE_SOR_CHEBY) {
+      // Red-black SOR with Chebyshev acceleration (not in the reference; README.md:39 asks for a better Poisson solver):
+      // the factor of colour half-sweep q is w_0 = 1, w_1 = 1/(1 - rho2/2), w_q = 1/(1 - rho2 w_{q-1}/4), with rho2 the
+      // squared Jacobi spectral radius behind the reference's omega (cavity-01.cpp:74-78).  Formulas: include/pm.h.
+      const double w_opt = o.c.omega, rho2 = pmi_cheby_rho2(w_opt);
+      for (int colour = 0; colour < 2; ++colour) {
+        const int q = 2 * (it - 1) + colour;
+        cheby_w = q == 0 ? 1.0 : pmi_cheby_next_omega(rho2, q, cheby_w);
+        o.c.omega = cheby_w;
+        sweep_inplace_rows(o, o.p, colour, 1, ny);
+      }
+      o.c.omega = w_opt;
     } else {
       sweep_jacobi_rows(o, o.p, tmp, 1, ny);
       // ghosts/solid cells of tmp carry over from the previous iterate until refreshed below

@@ -426,6 +426,48 @@ def test_large_grid_8192_tiled_equals_general_path(pm, exact):
     assert np.isfinite(out[0][1]).all() and np.abs(out[0][1]).max() > 0
 
 
+@pytest.mark.parametrize("exact", [1, 0])
+@pytest.mark.parametrize("case_id,nx,ny", CASES + [(0, 300, 200), (1, 260, 180), (2, 300, 90)])
+def test_cheby_sor_matches_oracle(pm, orc, case_id, nx, ny, exact):
+    """PM_PPE_SOR_CHEBY (relaxation factor moving with every colour half-sweep, include/pm.h) towards pm_omega_mixed_bc:
+    0 ulp against the oracle's restatement with exact arithmetic, whole steps; 1e-12 with production arithmetic."""
+    cfg = make_cfg(pm, case_id, nx, ny, 3, exact, 37)
+    cfg.omega = pm.lib().pm_omega_mixed_bc(case_id, nx, ny, cfg.dx, cfg.dy)
+    S, O = pm.Solver(cfg), orc.Oracle(cfg)
+    S.fill_random(13); O.fill_random(13)
+    S.apply_bc(0); O.apply_bc(0)
+    rs, ro = S.step(2), O.step(2)
+    assert rs.iterations == ro.iterations == 37
+    if exact:
+        assert rs.residual == ro.residual
+        assert_fields_equal(S, O, range(6), "cheby")
+    else:
+        assert abs(rs.residual - ro.residual) <= 1e-9 * ro.residual
+        assert_fields_close(S, O, range(6), 1e-12, "cheby, production arithmetic")
+
+
+@pytest.mark.parametrize("case_id,nx,ny", [(0, 64, 64), (1, 96, 32), (2, 128, 32)])
+def test_omega_mixed_converges_on_every_path_with_the_oracles_count(pm, orc, case_id, nx, ny):
+    """Red-black SOR with the mixed-BC factor run to the reference's tolerance: the persistent small-grid solve (AUTO), the
+    general path and the Chebyshev schedule stop on the oracle's iterate (exact arithmetic), several times earlier than with
+    the reference's factor."""
+    w = pm.lib().pm_omega_mixed_bc(case_id, nx, ny, pm.config_init(case_id, nx, ny).dx, pm.config_init(case_id, nx, ny).dy)
+    base = make_cfg(pm, case_id, nx, ny, RB, 1, 30000, path=0)
+    Sb = pm.Solver(base); Sb.fill_random(3, 2.0 ** -6); Sb.apply_bc(0)
+    rb = Sb.step(1)
+    Sb.close()
+    for method, path in ((RB, 0), (RB, 1), (3, 0)):
+        cfg = make_cfg(pm, case_id, nx, ny, method, 1, 30000, w, path=path)
+        S, O = pm.Solver(cfg), orc.Oracle(cfg)
+        S.fill_random(3, 2.0 ** -6); O.fill_random(3, 2.0 ** -6)
+        S.apply_bc(0); O.apply_bc(0)
+        rs, ro = S.step(1), O.step(1)
+        assert (rs.iterations, rs.residual, rs.hit_cap) == (ro.iterations, ro.residual, 0)
+        assert 2 * rs.iterations <= rb.iterations
+        assert_fields_equal(S, O, (0, 1, 2), f"omega mixed, method {method} path {path}")
+        S.close()
+
+
 def _stream_pair(pm, monkeypatch, cfg, seed, steps=1, prepare=None):
     """The same production red-black problem with the streaming pass (default) and with the tiled kernel alone."""
     out = []
