@@ -178,6 +178,8 @@ static void kp_set_omega(KP& k, double omega) {
   for (int n = 1; n <= 4; ++n) k.wnc[n] = omega / n;
   k.wnc[0] = 0.0;
   k.cw = k.case_id == PM_CASE_CAVITY ? omega * k.hh / 4.0 : omega / k.denom;
+  k.cw3 = omega * k.hh / 3.0;
+  k.cw2 = omega * k.hh / 2.0;
 }
 
 static void fill_kp(pm_solver* s, int j0, int nyl) {

@@ -31,6 +31,7 @@ struct KP {
   double wnc[5];                // cavity: omega / neighbor_count      (cavity-01.cpp:651)
   double denom, rdenom;         // channel: 2*(idx2+idy2), and its reciprocal for the fast policy
   double cw;                    // fast policy, residual form of the relaxation: p += cw * r  (cavity: omega*h*h/4; channel: omega/denom)
+  double cw3, cw2;              // cavity wall cells: omega*h*h / neighbor_count for 3 and 2 neighbours (cavity-01.cpp:644-651)
   double src_coef;              // cavity: (1/dt)*rho ; channel: rho/dt
   double cu, cv;                // correction coefficients
   double tol_factor, abs_tol;

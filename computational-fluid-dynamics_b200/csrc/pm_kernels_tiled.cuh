@@ -320,6 +320,27 @@ __device__ __forceinline__ void rb_half(const KP& k, double* tpx, double* tpy, C
       acc_max(PRE ? rmax_pre : post_raw, rs, out);
       continue;
     }
+    if (FORM == 0 && !INT && !A::exact) {
+      // Production arithmetic, cavity tiles at a wall: the same residual form.  A neighbour behind a wall (eps == 0,
+      // cavity-01.cpp:644-648) is replaced by the cell itself, so that  sum - 4 p  ==  sum over the real neighbours - nc p,
+      // and the relaxation factor is omega h^2 / nc; the residual after a colour-1 update is (1 - omega) r for every nc.
+      // One tree per cell instead of three (residual before, update, residual after): wall tiles were 3x slower than
+      // interior ones, and since the streaming pass they sit on the critical path of every pass.
+      const int ew = i > 1, ee = i < k.nx, en = j < k.ny;
+      const double pw_ = ew ? pw : pc, pe_ = ee ? pe : pc, pn_ = en ? pn : pc;
+      const double rs = fma(k.idx2, fma(-4.0, pc, (pe_ + pn_) + (pw_ + ps)), -fc);
+      const int nc = ew + ee + en;
+      const double cwc = nc == 3 ? k.cw : (nc == 2 ? k.cw3 : k.cw2);
+      const bool upd = commit && ((mW >> r) & 1u) && (tx ? colW0 : colW1);
+      if (upd) {
+        const double nvf = fma(cwc, rs, pc);
+        if (tx) c.p0[r] = nvf; else c.p1[r] = nvf;
+        cell[0] = nvf;
+      }
+      if (PRE) acc_max(rmax_pre, rs, out);
+      else acc_max(post_raw, rs, out && upd);
+      continue;
+    }
     if (PRE) acc_max(rmax_pre, cell_residual<A, FORM, INT>(k, j, i, pc, pe, pw, pn, ps, fc), out);
     const double nv = cell_update<A, FORM, INT>(k, j, i, pc, pe, pw, pn, ps, fc);
     if (INT) {
@@ -353,7 +374,7 @@ __device__ __forceinline__ void rb_half(const KP& k, double* tpx, double* tpy, C
       }
     }
   }
-  if (INT && !A::exact && POST) {
+  if ((INT || FORM == 0) && !A::exact && POST) {
     const double m = fabs(k.om1) * post_raw;  // residual of the iterate just created: (1 - omega) * r
     if (m > rmax_post) rmax_post = m;
   }
