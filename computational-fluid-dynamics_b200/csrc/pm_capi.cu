@@ -70,7 +70,8 @@ struct pm_solver {
   int last_iters = 0;
   bool use_tiled = false;
   bool use_small = false;  // persistent single-CTA solve (small grids)
-  bool no_cluster = false; // PM_NO_CLUSTER=1 in the environment: keep the persistent solve on one SM
+  bool no_cluster = false; // PM_NO_CLUSTER=1 in the environment (or no room for a cluster on this device): keep the persistent solve on one SM
+  bool cluster_checked = false;
   int sweeps = 1;
   int cheby_q = 0;       // PM_PPE_SOR_CHEBY: colour half-sweeps launched in this solve, and the factor of the last one
   double cheby_w = 1.0;
@@ -1072,13 +1073,14 @@ static const void* cluster_kernel(const KP& k) {
   if (k.has_mask) return reinterpret_cast<const void*>(&k_ppe_cluster<A, 1, true>);
   return reinterpret_cast<const void*>(&k_ppe_cluster<A, 1, false>);
 }
-// Small grids, red-black: the persistent solve on a cluster of 8 CTAs with DSMEM halo rows (k_ppe_cluster).
+// Small grids, red-black: the persistent solve on a cluster of PM_CLUSTER (16) CTAs with DSMEM halo rows (k_ppe_cluster).
 static int cluster_solve(pm_solver* s) {
   const KP& k = s->kp;
   const int nr_max = k.ny / PM_CLUSTER + (k.ny % PM_CLUSTER ? 1 : 0);
   const size_t smem = size_t(nr_max + 2) * size_t(k.nx + 2) * sizeof(double);
   const void* kern = s->cfg.exact_arith ? cluster_kernel<Exact>(k) : cluster_kernel<Fast>(k);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  if (PM_CLUSTER > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   // each thread keeps up to PM_CLUSTER_CPT cells per colour: enough threads for the band's half rows
   const int per_colour = nr_max * ((k.nx + 1) / 2);
   const int threads = std::min(512, std::max(64, (((per_colour + PM_CLUSTER_CPT - 1) / PM_CLUSTER_CPT + 31) / 32) * 32));
@@ -1098,6 +1100,16 @@ static int cluster_solve(pm_solver* s) {
   PpeState* st = s->d_state;
   unsigned long long* rb = s->d_res;
   void* args[] = {(void*)&k, (void*)&pg, (void*)&f, (void*)&m, (void*)&st, (void*)&rb};
+  if (!s->cluster_checked) {  // a cluster of 16 is a non-portable size: ask once whether this device can place one
+    int nclusters = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &lc);
+    s->cluster_checked = true;
+    if (e != cudaSuccess || nclusters < 1) {
+      (void)cudaGetLastError();
+      s->no_cluster = true;
+      return PM_ERR_UNSUPPORTED;  // small_solve falls back to the single-CTA solve
+    }
+  }
   CK(cudaLaunchKernelExC(&lc, kern, args));
   s->timing.kernel_launches++;
   s->timing.ppe_passes++;
@@ -1112,8 +1124,12 @@ static int small_solve(pm_solver* s, int* iters_out, double* res_out) {
     const int nr_max = k.ny / PM_CLUSTER + (k.ny % PM_CLUSTER ? 1 : 0);
     const size_t csmem = size_t(nr_max + 2) * size_t(k.nx + 2) * sizeof(double);
     const bool fits = nr_max * ((k.nx + 1) / 2) <= 512 * PM_CLUSTER_CPT;  // cells per colour and CTA held in registers
+    int cst = PM_ERR_UNSUPPORTED;
     if (s->cfg.ppe_method == PM_PPE_SOR_RB && k.ny >= 2 * PM_CLUSTER && csmem <= size_t(200) * 1024 && fits && !s->no_cluster) {
-      PMTRY(cluster_solve(s));
+      cst = cluster_solve(s);
+      if (cst != PM_OK && !(cst == PM_ERR_UNSUPPORTED && s->no_cluster)) return cst;
+    }
+    if (cst == PM_OK) {
       PMTRY(read_state(s));
       const int iters = s->h_state->iters;
       if (iters >= 1) {

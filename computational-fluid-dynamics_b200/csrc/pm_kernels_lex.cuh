@@ -367,13 +367,17 @@ __global__ void __launch_bounds__(1024, 1)
 // into its neighbours' halo rows (distributed shared memory: st.async, counted on an mbarrier of the receiving CTA)
 // and waits for its own halo rows to arrive -- no cluster barrier inside the loop (barrier.cluster's release costs a
 // MEMBAR.GPU: the pull-based version spent 3.7 us per iteration in three of them).  The per-CTA residual maxima travel
-// the same way to all eight CTAs, and every CTA evaluates the reference's loop test (cavity-01.cpp:635) on the same
+// the same way to all CTAs of the cluster, and every CTA evaluates the reference's loop test (cavity-01.cpp:635) on the same
 // number, so the cluster leaves the loop together.
 // ---------------------------------------------------------------------------
 #include <cooperative_groups.h>
 namespace pm_cg = cooperative_groups;
 
-#define PM_CLUSTER 8
+// CTAs per cluster.  Measured on configs[0..2] (us per iteration): one CTA 14.6 / 14.2 / 11.7, 4 CTAs 4.2 / 4.5 / 7.6,
+// 8 CTAs 2.9 / 3.2 / 6.5, 16 CTAs (a non-portable size: cudaFuncAttributeNonPortableClusterSizeAllowed) 2.4 / 2.4 / 4.6.
+#ifndef PM_CLUSTER
+#define PM_CLUSTER 16
+#endif
 
 __device__ __forceinline__ void pm_band(int ny, int c, int* ja, int* nr) {  // rows ja+1 .. ja+nr of the domain
   const int base = ny / PM_CLUSTER, rem = ny % PM_CLUSTER;
@@ -381,7 +385,9 @@ __device__ __forceinline__ void pm_band(int ny, int c, int* ja, int* nr) {  // r
   *ja = c * base + min(c, rem);
 }
 
-#define PM_CLUSTER_CPT 4  // cells per thread and colour (512 threads x 4 x 2 colours x 8 CTAs = 32 K cells)
+#ifndef PM_CLUSTER_CPT
+#define PM_CLUSTER_CPT 2  // cells per thread and colour (512 threads x 2 x 2 colours x 16 CTAs = 32 K cells)
+#endif
 
 template <class A, int FORM, bool MASK>
 __global__ void __launch_bounds__(512, 1)
@@ -389,7 +395,7 @@ __global__ void __launch_bounds__(512, 1)
                   PpeState* __restrict__ st, unsigned long long* __restrict__ res_bits) {
   extern __shared__ double smem[];
   __shared__ double red[32];
-  __shared__ __align__(16) double rslot[2][PM_CLUSTER];  // the eight CTAs' residual maxima, double-buffered by iteration parity
+  __shared__ __align__(16) double rslot[2][PM_CLUSTER];  // the CTAs' residual maxima, double-buffered by iteration parity
   __shared__ __align__(8) uint64_t hbar[3][2];           // halo rows arrived: [exchange: colour 0, colour 1, every cell][from below, from above]
   __shared__ __align__(8) uint64_t rbar[2];              // residual maxima arrived, by iteration parity
   pm_cg::cluster_group cluster = pm_cg::this_cluster();
