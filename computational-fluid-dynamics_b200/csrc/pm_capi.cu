@@ -681,6 +681,8 @@ extern "C" int pm_predict(pm_solver* s) {
   return PM_OK;
 }
 
+static int source_finish(pm_solver* s, int n_partial);
+
 extern "C" int pm_source(pm_solver* s) {
   if (!s) return PM_ERR_INVALID_ARGUMENT;
   CK(cudaSetDevice(s->device));
@@ -701,6 +703,15 @@ extern "C" int pm_source(pm_solver* s) {
     else k_source_rows<Fast, false><<<g, b, 0, s->stream>>>(k, s->pl[PL_US], s->pl[PL_VS], s->mask, s->pl[PL_F], s->d_state, partial);
   }
   CKL(s);
+  return source_finish(s, n_partial);
+}
+
+// What follows the pass that wrote f, max|f| and the per-block sums: the tolerance's max|f| (cavity), or the mean removal and
+// the max|f| behind it (channel / step; channel-01.cpp:621-628, :643-646).
+static int source_finish(pm_solver* s, int n_partial) {
+  const KP& k = s->kp;
+  const bool cav = k.case_id == PM_CASE_CAVITY;
+  const bool exact = s->cfg.exact_arith != 0;
   if (cav) {
     // the tolerance rule reads max|f| of this very pass (cavity-01.cpp:628-632)
     PMTRY(publish_words(s, &s->d_state->maxf2_bits, &s->d_state->maxf_bits, sizeof(unsigned long long)));
@@ -765,23 +776,30 @@ extern "C" int pm_source(pm_solver* s) {
   return PM_OK;
 }
 
-// Cavity: predictor and source in one pass (k_predict_source_cavity); what pm_predict followed by pm_source does.
+// Predictor and source in one pass: the cavity (nothing happens between them), and the channel without a mask (the boundary
+// values the source needs are taken inline; the caller runs pm_apply_bc(1) behind this for the stored u*, v*).
 static int predict_source_fused(pm_solver* s) {
   CK(cudaSetDevice(s->device));
   const KP& k = s->kp;
+  const bool cav = k.case_id == PM_CASE_CAVITY;
   PMTRY(exchange_halo1(s, s->pl[PL_U]));
   PMTRY(exchange_halo(s, s->pl[PL_V], 2, s->stream));  // the row below the slab is recomputed: it reads v two rows down
   CK(cudaMemsetAsync(&s->d_state->maxf_bits, 0, 2 * sizeof(unsigned long long), s->stream));
   const dim3 g(((k.nx + 1) / 2 + PM_RX - 1) / PM_RX, (k.nyl + PM_FUSE_ROWS - 1) / PM_FUSE_ROWS);
-  if (s->cfg.exact_arith)
-    k_predict_source_cavity<Exact><<<g, PM_RX, 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->pl[PL_US], s->pl[PL_VS], s->pl[PL_F], s->d_state);
-  else
-    k_predict_source_cavity<Fast><<<g, PM_RX, 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], s->pl[PL_US], s->pl[PL_VS], s->pl[PL_F], s->d_state);
+  const int n_partial = int(g.x * g.y);
+  double* partial = (!cav && !s->cfg.exact_arith) ? s->d_partial : nullptr;
+  if (partial && n_partial > s->cap_partial) return fail(s, PM_ERR_RUNTIME, "partial-sum buffer too small: %d blocks, %d slots", n_partial, s->cap_partial);
+  double *u = s->pl[PL_U], *v = s->pl[PL_V], *us = s->pl[PL_US], *vs = s->pl[PL_VS], *f = s->pl[PL_F];
+  if (cav) {
+    if (s->cfg.exact_arith) k_predict_source<Exact, 0><<<g, PM_RX, 0, s->stream>>>(k, u, v, us, vs, f, s->d_state, partial);
+    else k_predict_source<Fast, 0><<<g, PM_RX, 0, s->stream>>>(k, u, v, us, vs, f, s->d_state, partial);
+  } else {
+    if (s->cfg.exact_arith) k_predict_source<Exact, 1><<<g, PM_RX, 0, s->stream>>>(k, u, v, us, vs, f, s->d_state, partial);
+    else k_predict_source<Fast, 1><<<g, PM_RX, 0, s->stream>>>(k, u, v, us, vs, f, s->d_state, partial);
+  }
   CKL(s);
-  // the tolerance rule reads max|f| of this very pass (cavity-01.cpp:628-632)
-  PMTRY(publish_words(s, &s->d_state->maxf2_bits, &s->d_state->maxf_bits, sizeof(unsigned long long)));
-  s->f_max_valid = true;
-  return PM_OK;
+  if (!cav) PMTRY(pm_apply_bc(s, 1));
+  return source_finish(s, n_partial);
 }
 
 extern "C" int pm_correct(pm_solver* s) {
@@ -1295,9 +1313,13 @@ static int step_impl(pm_solver* s, int nsteps, pm_ppe_result* last) {
       PMTRY(pm_ppe_solve(s, &r));
       PMTRY(pm_correct(s));
     } else {  // channel-01.cpp:368-375
-      PMTRY(pm_predict(s));
-      PMTRY(pm_apply_bc(s, 1));
-      PMTRY(pm_source(s));
+      if (s->kp.case_id == PM_CASE_CHANNEL && (s->cfg.nranks == 1 || s->kp.nyl >= 2) && std::getenv("PM_NO_FUSE") == nullptr) {
+        PMTRY(predict_source_fused(s));  // predictor + the boundary values the source reads + source, then the BC kernel
+      } else {
+        PMTRY(pm_predict(s));
+        PMTRY(pm_apply_bc(s, 1));
+        PMTRY(pm_source(s));
+      }
       PMTRY(pm_ppe_solve(s, &r));
       PMTRY(pm_correct(s));
       PMTRY(pm_apply_bc(s, 0));

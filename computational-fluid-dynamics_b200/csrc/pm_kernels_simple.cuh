@@ -252,10 +252,15 @@ __global__ void __launch_bounds__(PM_RX* PM_RY)
 // row below the strip is recomputed once per strip.  Boundary faces the predictor never writes (u*[j][0], u*[j][nx],
 // v*[0][i], v*[ny][i]) are read from memory, exactly as the separate source pass would see them.
 #define PM_FUSE_ROWS 16
-template <class A>
+// FORM 1 (channel, no obstacle mask): the reference applies the boundary conditions to u*, v* between the two passes
+// (channel-01.cpp:368-371); the source only sees four of the values they set -- the inlet face u*[j][0] = U, the outlet
+// face u*[j][nx] = u*[j][nx-1], the wall faces v*[0][i] = v*[ny][i] = 0 (channel-01.cpp:513-529) -- and takes them inline;
+// k_bc_channel still runs behind this kernel for the stored u*, v*.  `partial`: one sum of f per block for the source mean.
+template <class A, int FORM>
 __global__ void __launch_bounds__(PM_RX)
-    k_predict_source_cavity(const __grid_constant__ KP k, const double* __restrict__ u, const double* __restrict__ v,
-                            double* __restrict__ us, double* __restrict__ vs, double* __restrict__ f, PpeState* __restrict__ st) {
+    k_predict_source(const __grid_constant__ KP k, const double* __restrict__ u, const double* __restrict__ v,
+                            double* __restrict__ us, double* __restrict__ vs, double* __restrict__ f, PpeState* __restrict__ st,
+                            double* __restrict__ partial) {
   __shared__ double s_ub[2][PM_RX];
   __shared__ double sh[32];
   const int tid = threadIdx.x;
@@ -264,14 +269,16 @@ __global__ void __launch_bounds__(PM_RX)
   const int P = k.pitch;
   const bool has = i <= k.nx, has_b = i + 1 <= k.nx;
   const bool a_u = i <= k.nx - 1, b_u = i + 1 <= k.nx - 1;  // columns whose u* the predictor writes
-  double a_max = 0.0;
+  double a_max = 0.0, f_sum = 0.0;
   double va_prev = 0.0, vb_prev = 0.0;  // v* of the row below the current one
   if (has) {
     const int jl = jl0 - 1, j = k.j0 + jl;
     const size_t c = pm_idx(k, jl, i);
     if (j == 0) {  // bottom wall faces: never written by the predictor
-      const double2 Vm = ld2(vs + c);
-      va_prev = Vm.x; vb_prev = Vm.y;
+      if (FORM == 0) {
+        const double2 Vm = ld2(vs + c);
+        va_prev = Vm.x; vb_prev = Vm.y;
+      }  // FORM 1: v*[0][i] = 0
     } else {       // last row of the strip below (another block writes it): same trees, same operands
       const double2 U = ld2(u + c), UN = ld2(u + c + P);
       const double2 V = ld2(v + c), VN = ld2(v + c + P), VS = ld2(v + c - P);
@@ -294,9 +301,9 @@ __global__ void __launch_bounds__(PM_RX)
       const bool a_v = j <= k.ny - 1;
       // u*: computed where the predictor writes, memory elsewhere (east wall face of the last column)
       if (a_u) ua = pred_u<A>(k, U.x, uW, U.y, UN.x, US.x, V.x, V.y, VS.x, VS.y);
-      else ua = us[c];
+      else if (FORM == 0) ua = us[c];  // FORM 1: the outlet face takes the value of the face to its west, below
       if (b_u) ub = pred_u<A>(k, U.y, U.x, uE2, UN.y, US.y, V.y, vE2, VS.y, vSE2);
-      else if (has_b) ub = us[c + 1];
+      else if (has_b) ub = FORM == 0 ? us[c + 1] : ua;
       if (a_u && b_u) st2(us + c, ua, ub);
       else if (a_u) us[c] = ua;
       if (a_v) {
@@ -304,12 +311,12 @@ __global__ void __launch_bounds__(PM_RX)
         vb = pred_v<A>(k, V.y, vE2, V.x, VN.y, VS.y, U.y, UN.y, U.x, UN.x);
         if (has_b) st2(vs + c, va, vb);
         else vs[c] = va;
-      } else {  // top wall faces
+      } else if (FORM == 0) {  // top wall faces
         const double2 Vm = ld2(vs + c);
         va = Vm.x; vb = Vm.y;
-      }
+      }  // FORM 1: v*[ny][i] = 0
       if (tid == 0) {  // u* of the column to the west of the block
-        if (i == 1) uw = us[c - 1];  // west wall face
+        if (i == 1) uw = FORM == 0 ? us[c - 1] : k.uref;  // west wall face / inlet face
         else uw = pred_u<A>(k, uW, u[c - 2], U.x, uNW, u[c - P - 1], vW, V.x, v[c - P - 1], VS.x);
       }
     }
@@ -317,14 +324,17 @@ __global__ void __launch_bounds__(PM_RX)
     __syncthreads();
     if (has) {
       if (tid > 0) uw = s_ub[r & 1][tid - 1];
+      if (FORM == 1 && !a_u) ua = uw;  // outlet face
       const double fa = A::mul(k.src_coef, A::add(A::mul(A::sub(ua, uw), k.idx), A::mul(A::sub(va, va_prev), k.idy)));
       if (has_b) {
         const double fb = A::mul(k.src_coef, A::add(A::mul(A::sub(ub, ua), k.idx), A::mul(A::sub(vb, vb_prev), k.idy)));
         st2(f + c, fa, fb);
         a_max = fmax(a_max, fmax(fabs(fa), fabs(fb)));
+        f_sum += fa + fb;
       } else {
         f[c] = fa;
         a_max = fmax(a_max, fabs(fa));
+        f_sum += fa;
       }
       va_prev = va;
       vb_prev = vb;
@@ -332,6 +342,10 @@ __global__ void __launch_bounds__(PM_RX)
   }
   const double m = block_max(a_max, sh);
   if (tid == 0) atomic_max_nonneg(&st->maxf_bits, m);
+  if (partial) {
+    const double sum = block_sum(f_sum, sh);
+    if (tid == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sum;
+  }
 }
 
 // k5 (fast policy): fixed-shape tree over the per-block partial sums, one block.

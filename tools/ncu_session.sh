@@ -7,7 +7,7 @@ $B > gpurun_out/${tag}_plain.json 2> gpurun_out/${tag}_plain.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv $B > gpurun_out/${tag}_ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_ppe_stream -s 30 -c 1 -f -o gpurun_out/${tag}_stream $B > gpurun_out/${tag}_ncu2.log 2>&1
 ncu --set full --clock-control none -k regex:k_ppe_tiled -s 30 -c 1 -f -o gpurun_out/${tag}_frame $B > gpurun_out/${tag}_ncu2b.log 2>&1
-ncu --set full --clock-control none -k regex:'k_predict_source_cavity|k_correct_rows|k_split_rows' -s 3 -c 3 -f -o gpurun_out/${tag}_other $B > gpurun_out/${tag}_ncu3.log 2>&1
+ncu --set full --clock-control none -k regex:'k_predict_source|k_correct_rows|k_split_rows' -s 3 -c 3 -f -o gpurun_out/${tag}_other $B > gpurun_out/${tag}_ncu3.log 2>&1
 ncu -i gpurun_out/${tag}_stream.ncu-rep --page raw --csv > gpurun_out/${tag}_stream_raw.csv 2>/dev/null
 ncu -i gpurun_out/${tag}_stream.ncu-rep --page source --csv > gpurun_out/${tag}_stream_source.csv 2>/dev/null
 ncu -i gpurun_out/${tag}_frame.ncu-rep --page raw --csv > gpurun_out/${tag}_frame_raw.csv 2>/dev/null
