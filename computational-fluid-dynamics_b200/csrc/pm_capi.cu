@@ -79,6 +79,7 @@ struct pm_solver {
   // streaming pass (pm_kernels_stream.cuh) over the interior tiles of the plan; f in the split-row layout for it
   StreamPlan splan{};
   double* fsplit = nullptr;
+  bool fsplit_valid = false;  // the fused predictor + source pass has just written fsplit along with f
   PmNccl nccl{};
   pm_timing timing{};
   HostPipe hp{};
@@ -790,12 +791,15 @@ static int predict_source_fused(pm_solver* s) {
   double* partial = (!cav && !s->cfg.exact_arith) ? s->d_partial : nullptr;
   if (partial && n_partial > s->cap_partial) return fail(s, PM_ERR_RUNTIME, "partial-sum buffer too small: %d blocks, %d slots", n_partial, s->cap_partial);
   double *u = s->pl[PL_U], *v = s->pl[PL_V], *us = s->pl[PL_US], *vs = s->pl[PL_VS], *f = s->pl[PL_F];
+  // single rank, cavity: f is final here, and the streaming pass never reads a ghost or pad row of it -> written split as well
+  double* fsp = (cav && s->splan.on && s->cfg.nranks == 1) ? s->fsplit : nullptr;
+  s->fsplit_valid = fsp != nullptr;
   if (cav) {
-    if (s->cfg.exact_arith) k_predict_source<Exact, 0><<<g, PM_RX, 0, s->stream>>>(k, u, v, us, vs, f, s->d_state, partial);
-    else k_predict_source<Fast, 0><<<g, PM_RX, 0, s->stream>>>(k, u, v, us, vs, f, s->d_state, partial);
+    if (s->cfg.exact_arith) k_predict_source<Exact, 0><<<g, PM_RX, 0, s->stream>>>(k, u, v, us, vs, f, s->d_state, partial, fsp);
+    else k_predict_source<Fast, 0><<<g, PM_RX, 0, s->stream>>>(k, u, v, us, vs, f, s->d_state, partial, fsp);
   } else {
-    if (s->cfg.exact_arith) k_predict_source<Exact, 1><<<g, PM_RX, 0, s->stream>>>(k, u, v, us, vs, f, s->d_state, partial);
-    else k_predict_source<Fast, 1><<<g, PM_RX, 0, s->stream>>>(k, u, v, us, vs, f, s->d_state, partial);
+    if (s->cfg.exact_arith) k_predict_source<Exact, 1><<<g, PM_RX, 0, s->stream>>>(k, u, v, us, vs, f, s->d_state, partial, fsp);
+    else k_predict_source<Fast, 1><<<g, PM_RX, 0, s->stream>>>(k, u, v, us, vs, f, s->d_state, partial, fsp);
   }
   CKL(s);
   if (!cav) PMTRY(pm_apply_bc(s, 1));
@@ -977,7 +981,8 @@ static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
     PMTRY(exchange_halo(s, s->pl[PL_F], pl.halo, s->stream));
     PMTRY(exchange_halo(s, pl.p[in0], pl.halo, s->stream));
   }
-  if (s->splan.on) PMTRY(convert_rows(s, s->pl[PL_F], s->fsplit, 1));  // f is constant over the solve
+  if (s->splan.on && !s->fsplit_valid) PMTRY(convert_rows(s, s->pl[PL_F], s->fsplit, 1));  // f is constant over the solve
+  s->fsplit_valid = false;  // whoever writes f next says so again
   int m = 0, n = 0;
   bool done = false;
   int chunk = s->cfg.poll_chunk > 0 ? s->cfg.poll_chunk : std::max(4, std::min(128, s->last_iters / (2 * T)));

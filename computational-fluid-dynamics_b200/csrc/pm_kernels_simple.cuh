@@ -260,7 +260,7 @@ template <class A, int FORM>
 __global__ void __launch_bounds__(PM_RX)
     k_predict_source(const __grid_constant__ KP k, const double* __restrict__ u, const double* __restrict__ v,
                             double* __restrict__ us, double* __restrict__ vs, double* __restrict__ f, PpeState* __restrict__ st,
-                            double* __restrict__ partial) {
+                            double* __restrict__ partial, double* __restrict__ fsplit /* f again in the split-row layout, or null */) {
   __shared__ double s_ub[2][PM_RX];
   __shared__ double sh[32];
   const int tid = threadIdx.x;
@@ -331,11 +331,15 @@ __global__ void __launch_bounds__(PM_RX)
         st2(f + c, fa, fb);
         a_max = fmax(a_max, fmax(fabs(fa), fabs(fb)));
         f_sum += fa + fb;
+        if (fsplit) fsplit[pm_sidx(k, jl, i + 1)] = fb;
       } else {
         f[c] = fa;
         a_max = fmax(a_max, fabs(fa));
         f_sum += fa;
       }
+      // the streaming pressure pass reads f in the layout of its p buffers (pm_common.cuh): saves a permutation pass
+      if (fsplit) fsplit[pm_sidx(k, jl, i)] = fa;
+
       va_prev = va;
       vb_prev = vb;
     }
