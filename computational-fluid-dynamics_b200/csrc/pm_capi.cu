@@ -427,6 +427,21 @@ extern "C" int pm_create(const pm_config* cfg, pm_solver** out) {
 }
 extern "C" int pm_destroy(pm_solver* s) { return destroy_impl(s); }
 
+// Host-only test hook: the streaming pass's plan for a slab of nyl rows starting at global row j0 of an nx x ny grid, tile rows
+// [row_lo, row_hi) (row_hi < 0: all), `slots` resident warps.  out[8] = {bx0, nbx, by0, nby, rows per chunk, chunks, warps,
+// frame tiles}.  Returns 1 if the pass streams, 0 if the tiled kernel keeps every tile.
+extern "C" int pm_stream_plan(int nx, int ny, int nyl, int j0, int row_lo, int row_hi, int slots, int* out) {
+  using C = TileCfg<PM_PPE_SOR_RB, 4>;
+  if (!out || nx < 1 || nyl < 1 || slots < 1) return -1;
+  const int tiles_x = (nx + C::TX - 1) / C::TX, tiles_y = (nyl + C::TY - 1) / C::TY;
+  if (row_hi < 0) row_hi = tiles_y;
+  StreamShape sh{};
+  if (!stream_shape(nx, ny, nyl, j0, tiles_x, row_lo, row_hi, C::TX, C::TY, C::SH, C::H, slots, 0, &sh)) return 0;
+  const int v[8] = {sh.bx0, sh.nbx, sh.by0, sh.nby, sh.rows, sh.nchunks, sh.items, sh.nframe};
+  for (int q = 0; q < 8; ++q) out[q] = v[q];
+  return 1;
+}
+
 extern "C" int pm_sync(pm_solver* s) {
   if (!s) return PM_ERR_INVALID_ARGUMENT;
   CK(cudaSetDevice(s->device));

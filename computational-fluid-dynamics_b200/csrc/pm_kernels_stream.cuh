@@ -339,29 +339,58 @@ static inline bool stream_supported(const pm_config& c, const KP& k, const Tiled
          std::getenv("PM_NO_STREAM") == nullptr;
 }
 
-static inline bool stream_create(StreamPlan* sp, const TiledPlan& pl, const pm_config& c, const KP& k, int row_lo, int row_hi, cudaStream_t stream,
-                                 std::string* err) {
-  sp->on = false;
-  const int H = pl.halo, SW = 128, SH = pl.sh;
-  auto x_ok = [&](int bx) { const int ib = 1 + bx * pl.tx - H; return ib + 1 >= 2 && ib + SW - 2 <= k.nx - 1; };
+// The plan's arithmetic, free of CUDA calls (pm_stream_plan exposes it to the CPU tests): the rectangle of tiles
+// [bx0, bx0 + nbx) x [by0, by0 + nby) inside the tile rows [row_lo, row_hi) whose tiles all satisfy k_ppe_tiled's `interior`
+// (separable in x and y), and the chunk height.
+struct StreamShape { int bx0, nbx, by0, nby, rows, nchunks, items, nframe; };
+static inline bool stream_shape(int nx, int ny, int nyl, int j0, int tiles_x, int row_lo, int row_hi, int tx, int ty, int sh, int H, int slots,
+                                int force_rows, StreamShape* o) {
+  const int SW = 128;
+  auto x_ok = [&](int bx) { const int ib = 1 + bx * tx - H; return ib + 1 >= 2 && ib + SW - 2 <= nx - 1; };
   auto y_ok = [&](int by) {
-    const int jb = 1 + by * pl.ty - H;
-    return k.j0 + jb + 1 >= 2 && k.j0 + jb + SH - 2 <= k.ny - 1 && jb + SH - 1 <= k.nyl + H && jb >= 1 - H;
+    const int jb = 1 + by * ty - H;
+    return j0 + jb + 1 >= 2 && j0 + jb + sh - 2 <= ny - 1 && jb + sh - 1 <= nyl + H && jb >= 1 - H;
   };
   int bx0 = -1, bx1 = -2, by0 = -1, by1 = -2;
-  for (int bx = 0; bx < pl.tiles_x; ++bx)
+  for (int bx = 0; bx < tiles_x; ++bx)
     if (x_ok(bx)) { if (bx0 < 0) bx0 = bx; bx1 = bx; }
   for (int by = row_lo; by < row_hi; ++by)
     if (y_ok(by)) { if (by0 < 0) by0 = by; by1 = by; }
   // (both predicates hold on one contiguous range)
   for (int bx = bx0; bx0 >= 0 && bx <= bx1; ++bx) if (!x_ok(bx)) { bx0 = -1; break; }
   for (int by = by0; by0 >= 0 && by <= by1; ++by) if (!y_ok(by)) { by0 = -1; break; }
-  if (bx0 < 0 || by0 < 0) return true;  // nothing to stream: the tiled kernel keeps every tile
+  if (bx0 < 0 || by0 < 0) return false;  // nothing to stream: the tiled kernel keeps every tile
   const int nbx = bx1 - bx0 + 1, nby = by1 - by0 + 1;
-  if (nbx * nby < 64) return true;
+  if (nbx * nby < 64) return false;
   // Chunk height: whole tile rows, and as few whole waves of warps as possible.  All warps of a wave run at the same
   // pace, so a launch that is a few warps over a wave takes a wave longer (measured at 8192^2: 1728 warps on 1776
   // slots 10.2 ms/step, 1872 warps 12.8); within that, the higher the chunk the less of it is spent on its 16 halo rows.
+  const int rows = nby * ty;
+  int best = ty;
+  double best_cost = 1e300;
+  for (int w = 1; w <= 64; ++w) {
+    const int nch_max = std::max(1, int((long long)w * slots / nbx));
+    int R = ((rows + nch_max - 1) / nch_max + ty - 1) / ty * ty;
+    R = std::min(R, rows);
+    const int nch = (rows + R - 1) / R;
+    if ((long long)nbx * nch > (long long)w * slots) continue;
+    const double cost = double(w) * (R + 2 * H + 8);
+    if (cost < best_cost) { best_cost = cost; best = R; }
+    if (R <= 2 * ty) break;
+  }
+  if (force_rows >= ty && force_rows % ty == 0) best = force_rows;
+  o->bx0 = bx0; o->nbx = nbx; o->by0 = by0; o->nby = nby;
+  o->rows = best;
+  o->nchunks = (rows + best - 1) / best;
+  o->items = nbx * o->nchunks;
+  o->nframe = (row_hi - row_lo) * tiles_x - nbx * nby;
+  return true;
+}
+
+static inline bool stream_create(StreamPlan* sp, const TiledPlan& pl, const pm_config& c, const KP& k, int row_lo, int row_hi, cudaStream_t stream,
+                                 std::string* err) {
+  sp->on = false;
+  const int H = pl.halo;
   int dev = 0, sms = 148, per_sm = PM_STREAM_MINB;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -370,23 +399,12 @@ static inline bool stream_create(StreamPlan* sp, const TiledPlan& pl, const pm_c
   cudaError_t e = cudaFuncSetAttribute(sp->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PM_STREAM_SMEM_BYTES);
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sp->kernel, 32, PM_STREAM_SMEM_BYTES);
   if (e != cudaSuccess || per_sm < 1) { *err = std::string("streaming kernel attributes: ") + cudaGetErrorString(e); return false; }
-  const int slots = sms * per_sm, rows = nby * pl.ty;
-  int best = pl.ty;
-  double best_cost = 1e300;
-  for (int w = 1; w <= 64; ++w) {
-    const int nch_max = std::max(1, int((long long)w * slots / nbx));
-    int R = ((rows + nch_max - 1) / nch_max + pl.ty - 1) / pl.ty * pl.ty;
-    R = std::min(R, rows);
-    const int nch = (rows + R - 1) / R;
-    if ((long long)nbx * nch > (long long)w * slots) continue;
-    const double cost = double(w) * (R + 2 * H + 8);
-    if (cost < best_cost) { best_cost = cost; best = R; }
-    if (R <= 2 * pl.ty) break;
-  }
-  if (const char* e = std::getenv("PM_STREAM_ROWS")) {
-    const int R = std::atoi(e);
-    if (R >= pl.ty && R % pl.ty == 0) best = R;
-  }
+  int force_rows = 0;
+  if (const char* ev = std::getenv("PM_STREAM_ROWS")) force_rows = std::atoi(ev);
+  StreamShape sh{};
+  if (!stream_shape(k.nx, k.ny, k.nyl, k.j0, pl.tiles_x, row_lo, row_hi, pl.tx, pl.ty, pl.sh, H, sms * per_sm, force_rows, &sh)) return true;
+  const int bx0 = sh.bx0, bx1 = sh.bx0 + sh.nbx - 1, by0 = sh.by0, by1 = sh.by0 + sh.nby - 1, nbx = sh.nbx, best = sh.rows;
+  const int rows = sh.nby * pl.ty;
   sp->g.bx0 = bx0; sp->g.nbx = nbx;
   sp->g.ya = 1 + by0 * pl.ty; sp->g.ye = 1 + (by1 + 1) * pl.ty;
   sp->g.rows = best;

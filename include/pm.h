@@ -160,6 +160,12 @@ double pm_cheby_omega(double omega, int q);
  * Not the default: the drivers take it with `--omega mixed` (and with `--ppe cheby`, whose schedule then tends to it). */
 double pm_omega_mixed_bc(int case_id, int nx, int ny, double dx, double dy);
 
+/* Host-only test hook (no device needed): how the streaming pressure pass would cut a slab of ny_local rows starting at global
+ * row j0 of an nx x ny grid into strips and chunks for `slots` resident warps, over the tile rows [row_lo, row_hi) of the
+ * tiled plan (row_hi < 0: all).  out[8] = {first strip, strips, first tile row, tile rows, rows per chunk, chunks, warps,
+ * tiles left to the tiled kernel}.  Returns 1 if the pass streams, 0 if not, -1 on bad arguments. */
+int pm_stream_plan(int nx, int ny, int ny_local, int j0, int row_lo, int row_hi, int slots, int* out);
+
 /* ---- lifetime ---------------------------------------------------------- */
 int pm_create(const pm_config* cfg, pm_solver** out);
 int pm_destroy(pm_solver* s);

@@ -121,3 +121,51 @@ def test_split_row_layout_properties(tmp_path):
     subprocess.run([nvcc, "-std=c++17", "-o", str(exe), src], check=True, capture_output=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "split layout ok" in out.stdout, out.stdout + out.stderr
+
+
+# ---- host logic of the streaming pressure pass (pm_kernels_stream.cuh, stream_shape) -------------------------------
+TX, TY, SH, H, SW = 112, 32, 48, 8, 128  # tile geometry of the red-black plan at T = 4 (pm_tile_cfg.cuh)
+
+
+def _interior(nx, ny, nyl, j0, bx, by):
+    """k_ppe_tiled's `interior` for an independent tile: every updatable cell strictly inside the domain, data for all neighbours."""
+    ib, jb = 1 + bx * TX - H, 1 + by * TY - H
+    return (ib + 1 >= 2 and ib + SW - 2 <= nx - 1 and j0 + jb + 1 >= 2 and j0 + jb + SH - 2 <= ny - 1
+            and jb + SH - 1 <= nyl + H and jb >= 1 - H)
+
+
+@pytest.mark.parametrize("nx,ny,nranks,slots", [(8192, 8192, 1, 1776), (16384, 16384, 1, 1776), (1400, 420, 1, 1776), (2000, 1500, 1, 1776),
+                                                 (16384, 16384 * 8, 8, 1776), (1400, 1408, 2, 1776), (1400, 1410, 2, 1184), (900, 300, 1, 1776)])
+def test_streaming_plan_arithmetic(pm, nx, ny, nranks, slots):
+    """The rectangle the streaming pass takes holds interior tiles only and cannot be widened; its chunks tile the rows; the
+    chunk height is the cheapest under the wave model the plan states (whole waves of `slots` warps, rows + 24 ticks each)."""
+    L = pm.lib()
+    for rank in sorted({0, nranks // 2, nranks - 1}):
+        j0, nyl = C.c_int(), C.c_int()
+        assert L.pm_slab_range(ny, nranks, rank, C.byref(j0), C.byref(nyl)) == 0
+        j0, nyl = j0.value, nyl.value
+        tiles_x, tiles_y = -(-nx // TX), -(-nyl // TY)
+        row_lo, row_hi = 0, tiles_y
+        if nranks > 1:  # edge tile rows go ahead of the rest (slab_edge_rows in pm_capi.cu)
+            top = 1
+            while top < tiles_y and nyl - (tiles_y - top) * TY < H:
+                top += 1
+            row_lo, row_hi = 1, tiles_y - top
+        out = (C.c_int * 8)()
+        on = L.pm_stream_plan(nx, ny, nyl, j0, row_lo, row_hi, slots, out)
+        ok = [[_interior(nx, ny, nyl, j0, bx, by) for bx in range(tiles_x)] for by in range(tiles_y)]
+        if not on:
+            assert sum(ok[by][bx] for by in range(row_lo, row_hi) for bx in range(tiles_x)) < 64 or nx < 400
+            continue
+        bx0, nbx, by0, nby, rows, nch, items, nframe = list(out)
+        assert all(ok[by][bx] for by in range(by0, by0 + nby) for bx in range(bx0, bx0 + nbx))
+        assert by0 >= row_lo and by0 + nby <= row_hi
+        assert (bx0 == 0 or not ok[by0][bx0 - 1]) and (bx0 + nbx == tiles_x or not ok[by0][bx0 + nbx])
+        assert (by0 == row_lo or not ok[by0 - 1][bx0]) and (by0 + nby == row_hi or not ok[by0 + nby][bx0])
+        assert nframe == (row_hi - row_lo) * tiles_x - nbx * nby
+        total = nby * TY
+        assert rows % TY == 0 and nch * rows >= total > (nch - 1) * rows and items == nbx * nch
+        cost = lambda R: -(-(nbx * -(-total // R)) // slots) * (R + 2 * H + 8)
+        assert cost(rows) == min(cost(R) for R in range(TY, total + 1, TY))
+    if (nx, ny, nranks) == (8192, 8192, 1):
+        assert (bx0, nbx, by0, nby, rows, items) == (1, 72, 1, 254, 352, 1728)  # the measured launch shape (DESIGN 5a)
