@@ -77,6 +77,16 @@ struct pm_solver {
   double cheby_w = 1.0;
   TiledPlan tiled{};
   // streaming pass (pm_kernels_stream.cuh) over the interior tiles of the plan; f in the split-row layout for it
+  // PM_TRACE_PASS=1: device timestamps of the pieces of every pass of the slab path (tiled_pass), summed per solve and
+  // printed by pm_destroy -- a text timeline of a pass (profiles/r02_pass_timeline_*.txt)
+  struct PassTrace {
+    bool on = false;
+    static constexpr int NEV = 7, CAP = 64;  // events per pass: start, edge rows, halo rows, frame, interior, fold, allreduce
+    cudaEvent_t ev[CAP][NEV] = {};
+    int used = 0;
+    double sum_us[NEV] = {};
+    long long passes = 0;
+  } trace;
   StreamPlan splan{};
   double* fsplit = nullptr;
   bool fsplit_valid = false;  // the fused predictor + source pass has just written fsplit along with f
@@ -259,6 +269,20 @@ static int destroy_impl(pm_solver* s) {
     cudaStreamDestroy(s->hp.d2h);
     cudaFree(s->hp.extra);
   }
+  if (s->trace.on) {
+    const auto& t = s->trace;
+    if (t.passes > 0) {
+      const double n = double(t.passes);
+      fprintf(stderr,
+              "[pm] rank %d of %d, %lld streamed passes, microseconds from the start of a pass (averages): edge tile rows done %.1f | "
+              "halo rows exchanged %.1f | wall tiles of the middle rows done %.1f | streaming kernel done %.1f | residual slots folded %.1f | "
+              "allreduce(max) of the residual words done = end of pass %.1f\n",
+              s->cfg.rank, s->cfg.nranks, t.passes, t.sum_us[1] / n, t.sum_us[2] / n, t.sum_us[3] / n, t.sum_us[4] / n, t.sum_us[5] / n, t.sum_us[6] / n);
+    }
+    for (auto& row : s->trace.ev)
+      for (cudaEvent_t ev : row)
+        if (ev) cudaEventDestroy(ev);
+  }
   if (s->base) cudaFree(s->base);
   if (s->tp[0]) cudaFree(s->tp[0]);
   if (s->fsplit) cudaFree(s->fsplit);
@@ -364,6 +388,11 @@ static int create_impl(pm_solver* s, const pm_config* cfg) {
       return fail(s, PM_ERR_CUDA, "tiled path setup: %s", e.c_str());
     s->sweeps = s->tiled.run;
     s->kp.psh = s->tiled.psh;
+    if (std::getenv("PM_TRACE_PASS") != nullptr && c.nranks > 1) {
+      for (auto& row : s->trace.ev)
+        for (cudaEvent_t& ev : row) CK(cudaEventCreate(&ev));
+      s->trace.on = true;
+    }
     if (stream_supported(c, s->kp, s->tiled)) {
       int bot = 0, top = 0;
       slab_edge_rows(s, &bot, &top);
@@ -925,6 +954,23 @@ static int read_state(pm_solver* s) {
 // Slabs: the tile rows whose output the neighbours need (within H rows of the slab edge) are launched
 // first; their H halo rows travel by ncclSend/ncclRecv on the comm stream while the interior tile rows
 // run; the residual maxima of the pass are max-allreduced in stream order before the next pass tests them.
+static void trace_mark(pm_solver* s, int slot, int which, cudaStream_t st) {
+  if (slot >= 0) cudaEventRecord(s->trace.ev[slot][which], st);
+}
+// After a synchronisation of every stream: fold the recorded passes into the sums.
+static void trace_collect(pm_solver* s) {
+  auto& t = s->trace;
+  for (int q = 0; q < t.used; ++q) {
+    for (int w = 1; w < t.NEV; ++w) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, t.ev[q][0], t.ev[q][w]) == cudaSuccess) t.sum_us[w] += 1e3 * ms;
+      else (void)cudaGetLastError();
+    }
+    ++t.passes;
+  }
+  t.used = 0;
+}
+
 static int tiled_pass(pm_solver* s, int in, int m0, int nsw, int force) {
   const KP& k = s->kp;
   const TiledPlan& pl = s->tiled;
@@ -953,21 +999,27 @@ static int tiled_pass(pm_solver* s, int in, int m0, int nsw, int force) {
     // The edge tile rows go out on a high-priority stream and the interior rows on the main stream at the same time:
     // the edge CTAs are scheduled first, the interior ones fill the rest of the machine (two edge launches alone would
     // leave half of it idle), and the halo rows travel while the interior is still being swept.
+    const int tr = (s->trace.on && streamed && s->trace.used < s->trace.CAP) ? s->trace.used++ : -1;
+    trace_mark(s, tr, 0, s->stream);
     CK(cudaEventRecord(s->ev_pass, s->stream));
     CK(cudaStreamWaitEvent(s->edge_stream, s->ev_pass, 0));
     CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, 0, bot, s->edge_stream));
     CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, pl.tiles_y - top, top, s->edge_stream));
     s->timing.kernel_launches += 2;
     CK(cudaEventRecord(s->ev_edge, s->edge_stream));
+    trace_mark(s, tr, 1, s->edge_stream);
     if (nsw > 0) {
       CK(cudaStreamWaitEvent(s->comm_stream, s->ev_edge, 0));
       PMTRY(exchange_halo(s, pl.p[in ^ 1], pl.halo, s->comm_stream));
       CK(cudaEventRecord(s->ev_halo, s->comm_stream));
+      trace_mark(s, tr, 2, s->comm_stream);
     }
     if (streamed) {  // the frame of the middle rows behind the edge rows on their stream, the rectangle on the main stream
       CK(tiled_launch_list(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, sp.frame, sp.nframe, s->edge_stream));
       CK(cudaEventRecord(s->ev_edge, s->edge_stream));
+      trace_mark(s, tr, 3, s->edge_stream);
       CK(stream_launch(&sp, &pl, k, in, s->fsplit, s->d_state, s->d_res, m0, force, s->stream));
+      trace_mark(s, tr, 4, s->stream);
       s->timing.kernel_launches += 2;
     } else {
       CK(tiled_launch(&pl, k, in, f, s->d_state, s->d_res, m0, nsw, force, bot, pl.tiles_y - bot - top, s->stream));
@@ -975,6 +1027,16 @@ static int tiled_pass(pm_solver* s, int in, int m0, int nsw, int force) {
     }
     CK(cudaStreamWaitEvent(s->stream, s->ev_edge, 0));
     if (nsw > 0) CK(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+    CK(tiled_fold_launch(&pl, k, s->d_res, m0, nsw, s->stream));
+    s->timing.kernel_launches++;
+    trace_mark(s, tr, 5, s->stream);
+    if (!force) {
+      const int lo = std::max(m0, 1), hi = m0 + std::max(nsw, 1) - 1;
+      PMTRY(allreduce_res(s, lo, hi - lo + 1));
+    }
+    trace_mark(s, tr, 6, s->stream);
+    s->timing.ppe_passes++;
+    return PM_OK;
   }
   // entries m0 .. m0+max(nsw,1)-1 are now complete on this rank (both colour parts): slots -> res_bits
   CK(tiled_fold_launch(&pl, k, s->d_res, m0, nsw, s->stream));
@@ -1039,6 +1101,10 @@ static int tiled_solve(pm_solver* s, int* iters_out, double* res_out) {
     std::memcpy(res_out, s->h_res, 8);
   } else {
     *res_out = s->h_state->res_init;
+  }
+  if (s->trace.on) {
+    CK(cudaStreamSynchronize(s->stream));
+    trace_collect(s);
   }
   *iters_out = iters;
   return PM_OK;
