@@ -54,6 +54,8 @@ def main():
         (pm.CASE_CAVITY, 1100, 600, pm.PPE_SOR_RB, 1, pm.PATH_TILED, 4, 22, 1),   # deepest halo (8 rows = all pad rows)
         (pm.CASE_CHANNEL, 600, 333, pm.PPE_SOR_RB, 0, pm.PATH_AUTO, 0, 21, 2),    # production path as the drivers run it: T = 4, split-row buffers, row kernels
         (pm.CASE_CAVITY, 64, 64, pm.PPE_SOR_RB, 1, pm.PATH_SIMPLE, 0, 10000, 2),  # run to tolerance: same stopping iterate
+        (pm.CASE_CAVITY, 200, 70, pm.PPE_SOR_RB, 1, pm.PATH_TILED, 3, 20000, 1),  # ... on the tiled path: device-side loop test over slabs, replay of the partial pass
+        (pm.CASE_CHANNEL, 200, 60, pm.PPE_SOR_RB, 0, pm.PATH_TILED, 4, 30000, 1),
         # exact arithmetic for channel/step: the reference's serial source mean is continued from slab to slab
         (pm.CASE_CHANNEL, 300, 50, pm.PPE_SOR_RB, 1, pm.PATH_SIMPLE, 0, 30, 2),
         (pm.CASE_CHANNEL, 300, 50, pm.PPE_SOR_RB, 1, pm.PATH_TILED, 4, 30, 2),
