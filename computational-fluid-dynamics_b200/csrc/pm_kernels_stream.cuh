@@ -401,8 +401,10 @@ static inline bool stream_create(StreamPlan* sp, const TiledPlan& pl, const pm_c
   if (e != cudaSuccess || per_sm < 1) { *err = std::string("streaming kernel attributes: ") + cudaGetErrorString(e); return false; }
   int force_rows = 0;
   if (const char* ev = std::getenv("PM_STREAM_ROWS")) force_rows = std::atoi(ev);
+  int slots = sms * per_sm;
+  if (const char* ev = std::getenv("PM_STREAM_SLOTS")) { const int v = std::atoi(ev); if (v > 0) slots = v; }
   StreamShape sh{};
-  if (!stream_shape(k.nx, k.ny, k.nyl, k.j0, pl.tiles_x, row_lo, row_hi, pl.tx, pl.ty, pl.sh, H, sms * per_sm, force_rows, &sh)) return true;
+  if (!stream_shape(k.nx, k.ny, k.nyl, k.j0, pl.tiles_x, row_lo, row_hi, pl.tx, pl.ty, pl.sh, H, slots, force_rows, &sh)) return true;
   const int bx0 = sh.bx0, bx1 = sh.bx0 + sh.nbx - 1, by0 = sh.by0, by1 = sh.by0 + sh.nby - 1, nbx = sh.nbx, best = sh.rows;
   const int rows = sh.nby * pl.ty;
   sp->g.bx0 = bx0; sp->g.nbx = nbx;
