@@ -125,31 +125,15 @@ void check(int status, pm_solver* s, const char* what) {
   throw std::runtime_error(msg && *msg ? std::string(msg) : std::string(what) + ": " + pm_status_string(status));
 }
 
-// ---- host-side view of the downloaded fields (only touched at print/save intervals) ----
+// ---- host-side view of what a frame prints (only touched at save intervals): five dense ny x nx arrays formed on the
+// device by pm_export_begin / pm_export_wait (cell-centre velocities, magnitude, pressure, vorticity) and the fluid mask ----
 struct Snapshot {
   int nx = 0, ny = 0;
-  std::vector<double> u, v, p, uc, vc;
+  std::vector<double> uc, vc, mag, p, vort;
   std::vector<uint8_t> fluid;
-  double U(int j, int i) const { return u[size_t(j) * (nx + 1) + i]; }
-  double V(int j, int i) const { return v[size_t(j) * (nx + 2) + i]; }
-  double P(int j, int i) const { return p[size_t(j) * (nx + 2) + i]; }
-  double Uc(int j, int i) const { return uc[size_t(j) * (nx + 2) + i]; }
-  double Vc(int j, int i) const { return vc[size_t(j) * (nx + 2) + i]; }
+  size_t at(int j, int i) const { return size_t(j - 1) * nx + (i - 1); }
   bool F(int j, int i) const { return fluid[size_t(j) * (nx + 2) + i] != 0; }
 };
-
-// interpolateToCellCenters (cavity-01.cpp:717-733; backwards_step-01.cpp:981-1009: solid cells stay 0)
-void centres(const pm_config& c, Snapshot& sn) {
-  const int nx = c.nx, ny = c.ny;
-  sn.uc.assign(size_t(ny + 2) * (nx + 2), 0.0);
-  sn.vc.assign(size_t(ny + 2) * (nx + 2), 0.0);
-  for (int j = 1; j <= ny; ++j)
-    for (int i = 1; i <= nx; ++i) {
-      if (!sn.F(j, i)) continue;
-      sn.uc[size_t(j) * (nx + 2) + i] = 0.5 * (sn.U(j, i - 1) + sn.U(j, i));
-      sn.vc[size_t(j) * (nx + 2) + i] = 0.5 * (sn.V(j - 1, i) + sn.V(j, i));
-    }
-}
 
 // Legacy-VTK STRUCTURED_POINTS writer; text identical to the reference writers
 // (cavity-01.cpp:95-231; channel-01.cpp:88-190; backwards_step-01.cpp:89-220): every double goes through the
@@ -175,50 +159,36 @@ void write_vtk(const std::string& path, const pm_config& c, const Snapshot& sn, 
   for (int j = 1; j <= ny; ++j)
     for (int i = 1; i <= nx; ++i) {
       if (step && !sn.F(j, i)) std::fprintf(f, "0.0 0.0 0.0\n");
-      else std::fprintf(f, "%.6f %.6f 0.0\n", sn.Uc(j, i), sn.Vc(j, i));
+      else std::fprintf(f, "%.6f %.6f 0.0\n", sn.uc[sn.at(j, i)], sn.vc[sn.at(j, i)]);
     }
+  // solid cells hold 0 in every exported array (interpolateToCellCenters leaves them 0, the writers print 0.0 for them)
   std::fprintf(f, "SCALARS u_velocity double 1\nLOOKUP_TABLE default\n");
   for (int j = 1; j <= ny; ++j)
-    for (int i = 1; i <= nx; ++i) std::fprintf(f, "%.6f\n", (!step || sn.F(j, i)) ? sn.Uc(j, i) : 0.0);
+    for (int i = 1; i <= nx; ++i) std::fprintf(f, "%.6f\n", sn.uc[sn.at(j, i)]);
   std::fprintf(f, "SCALARS v_velocity double 1\nLOOKUP_TABLE default\n");
   for (int j = 1; j <= ny; ++j)
-    for (int i = 1; i <= nx; ++i) std::fprintf(f, "%.6f\n", (!step || sn.F(j, i)) ? sn.Vc(j, i) : 0.0);
+    for (int i = 1; i <= nx; ++i) std::fprintf(f, "%.6f\n", sn.vc[sn.at(j, i)]);
   std::fprintf(f, "SCALARS velocity_magnitude double 1\nLOOKUP_TABLE default\n");
   for (int j = 1; j <= ny; ++j)
     for (int i = 1; i <= nx; ++i) {
       if (step && !sn.F(j, i)) { std::fprintf(f, "0.0\n"); continue; }
-      std::fprintf(f, "%.6f\n", std::sqrt(sn.Uc(j, i) * sn.Uc(j, i) + sn.Vc(j, i) * sn.Vc(j, i)));
+      std::fprintf(f, "%.6f\n", sn.mag[sn.at(j, i)]);
     }
   std::fprintf(f, "SCALARS pressure double 1\nLOOKUP_TABLE default\n");
   for (int j = 1; j <= ny; ++j)
-    for (int i = 1; i <= nx; ++i) std::fprintf(f, "%.6f\n", (!step || sn.F(j, i)) ? sn.P(j, i) : 0.0);
+    for (int i = 1; i <= nx; ++i) std::fprintf(f, "%.6f\n", sn.p[sn.at(j, i)]);
+  // vorticity: formed on the device with the writers' own expression trees (cavity-01.cpp:187-223: one-sided at the edges,
+  // (diff * dx_inv) * 0.5 inside; channel-01.cpp:171-182: (0.5 * diff) * idx; backwards_step-01.cpp:203-236: only where the
+  // cell and its four neighbours are fluid and off the domain edge -- elsewhere that writer prints the literal 0.0)
   std::fprintf(f, "SCALARS vorticity double 1\nLOOKUP_TABLE default\n");
-  const double idx = 1.0 / c.dx, idy = 1.0 / c.dy;
   for (int j = 1; j <= ny; ++j)
     for (int i = 1; i <= nx; ++i) {
-      double dvdx, dudy;
-      if (cs == PM_CASE_CAVITY) {  // one-sided at the edges, (diff * dx_inv) * 0.5 inside, cavity-01.cpp:187-223
-        if (i == 1) dvdx = (sn.Vc(j, i + 1) - sn.Vc(j, i)) * idx;
-        else if (i == nx) dvdx = (sn.Vc(j, i) - sn.Vc(j, i - 1)) * idx;
-        else dvdx = (sn.Vc(j, i + 1) - sn.Vc(j, i - 1)) * idx * 0.5;
-        if (j == 1) dudy = (sn.Uc(j + 1, i) - sn.Uc(j, i)) * idx;
-        else if (j == ny) dudy = (sn.Uc(j, i) - sn.Uc(j - 1, i)) * idx;
-        else dudy = (sn.Uc(j + 1, i) - sn.Uc(j - 1, i)) * idx * 0.5;
-      } else if (cs == PM_CASE_CHANNEL) {  // (0.5 * diff) * idx inside, channel-01.cpp:171-182
-        if (i == 1) dvdx = (sn.Vc(j, i + 1) - sn.Vc(j, i)) * idx;
-        else if (i == nx) dvdx = (sn.Vc(j, i) - sn.Vc(j, i - 1)) * idx;
-        else dvdx = 0.5 * (sn.Vc(j, i + 1) - sn.Vc(j, i - 1)) * idx;
-        if (j == 1) dudy = (sn.Uc(j + 1, i) - sn.Uc(j, i)) * idy;
-        else if (j == ny) dudy = (sn.Uc(j, i) - sn.Uc(j - 1, i)) * idy;
-        else dudy = 0.5 * (sn.Uc(j + 1, i) - sn.Uc(j - 1, i)) * idy;
-      } else {  // only where all four neighbours are fluid and off the domain edge, backwards_step-01.cpp:203-236
+      if (step) {
         bool ok = sn.F(j, i) && !(i == 1 || i == nx || j == 1 || j == ny);
         if (ok && (!sn.F(j, i - 1) || !sn.F(j, i + 1) || !sn.F(j - 1, i) || !sn.F(j + 1, i))) ok = false;
         if (!ok) { std::fprintf(f, "0.0\n"); continue; }
-        dvdx = 0.5 * (sn.Vc(j, i + 1) - sn.Vc(j, i - 1)) * idx;
-        dudy = 0.5 * (sn.Uc(j + 1, i) - sn.Uc(j - 1, i)) * idy;
       }
-      std::fprintf(f, "%.6f\n", dvdx - dudy);
+      std::fprintf(f, "%.6f\n", sn.vort[sn.at(j, i)]);
     }
   const bool bad = std::ferror(f) != 0;
   if (std::fclose(f) != 0 || bad) throw std::runtime_error("Error writing to file: " + path);
@@ -264,31 +234,45 @@ struct Run {
 
   void sync_ranks() { if (bar) bar->wait(); }
 
-  void export_frame(int step, double t) {
+  // A frame is taken in two halves: export_begin enqueues the device-side export (kernel + copy to pinned host memory on its
+  // own stream) behind the current state; export_flush waits for it, and rank 0 writes the file.  Inside the time loop the
+  // flush comes after the NEXT step has been issued, so the copy overlaps that step; the order of the lines on stdout
+  // stays the reference's (the "Exported" line precedes everything the next step prints).
+  struct Pending { bool active = false; int step = 0; double t = 0.0; } pend;
+
+  void export_begin(int step, double t) {
     if (!opt.vtk) return;
+    export_flush();
+    try {
+      check(pm_export_begin(s), s, "export");
+      pend.active = true; pend.step = step; pend.t = t;
+    } catch (const std::exception& e) {  // an export failure is logged, the run goes on (cavity-01.cpp:479-481)
+      std::fprintf(stderr, "%sError exporting VTK data: %s%s\n", RED, e.what(), RESET);
+    }
+  }
+
+  void export_flush() {
+    if (!opt.vtk || !pend.active) return;
+    pend.active = false;
     Snapshot& sn = shared ? *shared : snap;
     try {
       char name[256];
-      std::snprintf(name, sizeof name, "%s_%06d.vtk", kText[cfg.case_id].vtk_base, step);
-      if (rank == 0) {  // size the host arrays once; pm_download then fills only the caller's rows
+      std::snprintf(name, sizeof name, "%s_%06d.vtk", kText[cfg.case_id].vtk_base, pend.step);
+      if (rank == 0) {  // size the host arrays once; pm_export_wait then fills only the caller's rows
         sn.nx = cfg.nx; sn.ny = cfg.ny;
-        sn.u.resize(size_t(cfg.ny + 2) * (cfg.nx + 1));
-        sn.v.resize(size_t(cfg.ny + 1) * (cfg.nx + 2));
-        sn.p.resize(size_t(cfg.ny + 2) * (cfg.nx + 2));
+        const size_t n = size_t(cfg.nx) * cfg.ny;
+        for (std::vector<double>* a : {&sn.uc, &sn.vc, &sn.mag, &sn.p, &sn.vort}) a->resize(n);
       }
       sync_ranks();
-      check(pm_download(s, PM_FIELD_U, sn.u.data(), sn.u.size()), s, "download u");
-      check(pm_download(s, PM_FIELD_V, sn.v.data(), sn.v.size()), s, "download v");
-      check(pm_download(s, PM_FIELD_P, sn.p.data(), sn.p.size()), s, "download p");
+      check(pm_export_wait(s, sn.uc.data(), sn.vc.data(), sn.mag.data(), sn.p.data(), sn.vort.data(), sn.uc.size()), s, "export");
       sync_ranks();
       if (rank == 0) {
-        centres(cfg, sn);
-        write_vtk(opt.outdir + "/" + name, cfg, sn, t);
+        write_vtk(opt.outdir + "/" + name, cfg, sn, pend.t);
         files.emplace_back(name);
-        times.push_back(t);
-        if (step % print_interval == 0 || step == 0) std::printf("%sExported VTK file: %s%s\n", BLUE, name, RESET);
+        times.push_back(pend.t);
+        if (pend.step % print_interval == 0 || pend.step == 0) std::printf("%sExported VTK file: %s%s\n", BLUE, name, RESET);
       }
-    } catch (const std::exception& e) {  // an export failure is logged, the run goes on (cavity-01.cpp:479-481)
+    } catch (const std::exception& e) {
       std::fprintf(stderr, "%sError exporting VTK data: %s%s\n", RED, e.what(), RESET);
     }
     sync_ranks();
@@ -352,13 +336,15 @@ struct Run {
     // frame 0: the channel/step constructors and the cavity's run() apply the BCs and export before stepping
     if (root && cs == PM_CASE_CAVITY) std::printf("%s%s%s", GREEN, kText[cs].start_msg, RESET);
     check(pm_apply_bc(s, 0), s, "apply_bc");
-    export_frame(0, 0.0);
+    export_begin(0, 0.0);
+    export_flush();
     if (root && cs != PM_CASE_CAVITY) std::printf("%s%s%s", GREEN, kText[cs].start_msg, RESET);
 
     for (int step = 1; step <= total_steps; ++step) {
       const double t = step * cfg.dt;
       pm_ppe_result r{};
       check(pm_step(s, 1, &r), s, "step");
+      export_flush();  // the frame taken after the previous step, if any: its copy ran beside this step
       if (root && r.hit_cap) {
         if (cs == PM_CASE_CAVITY)
           std::fprintf(stderr, "Warning: SOR solver did not converge in %d iterations. Final residual: %g\n", cfg.max_iters, r.residual);
@@ -366,9 +352,10 @@ struct Run {
           std::fprintf(stderr, "%sWarning: PPE SOR hit max iterations, max_res=%g%s\n", YELLOW, r.residual, RESET);
       }
       if (step % print_interval == 0 || step == total_steps) log_line(step, t, r);
-      if (step % save_interval == 0 || step == total_steps) export_frame(step, t);
+      if (step % save_interval == 0 || step == total_steps) export_begin(step, t);
       if (opt.stop_after > 0 && step >= opt.stop_after) break;
     }
+    export_flush();
     if (root && opt.vtk) {
       try {
         const std::string pvd = std::string(kText[cs].vtk_base) + "_animation.pvd";

@@ -87,6 +87,14 @@ struct pm_solver {
     double sum_us[NEV] = {};
     long long passes = 0;
   } trace;
+  // device-side export (pm_export_begin / pm_export_wait): dense staging on the device and in pinned host memory
+  struct Export {
+    double* dev = nullptr;
+    double* host = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ready = nullptr, done = nullptr;
+    bool pending = false;
+  } ex;
   StreamPlan splan{};
   double* fsplit = nullptr;
   bool fsplit_valid = false;  // the fused predictor + source pass has just written fsplit along with f
@@ -283,6 +291,11 @@ static int destroy_impl(pm_solver* s) {
       for (cudaEvent_t ev : row)
         if (ev) cudaEventDestroy(ev);
   }
+  if (s->ex.dev) cudaFree(s->ex.dev);
+  if (s->ex.host) cudaFreeHost(s->ex.host);
+  if (s->ex.ready) cudaEventDestroy(s->ex.ready);
+  if (s->ex.done) cudaEventDestroy(s->ex.done);
+  if (s->ex.stream) cudaStreamDestroy(s->ex.stream);
   if (s->base) cudaFree(s->base);
   if (s->tp[0]) cudaFree(s->tp[0]);
   if (s->fsplit) cudaFree(s->fsplit);
@@ -1555,6 +1568,53 @@ extern "C" int pm_diagnostics(pm_solver* s, double* max_div, double* avg_ke) {
   const double ke = s->h_state->ke_sum;
   if (k.case_id == PM_CASE_STEP) *avg_ke = k.fluid_count_global > 0 ? ke / k.fluid_count_global : 0.0;
   else *avg_ke = ke / (k.nx * k.ny);
+  return PM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// export: what the VTK writers print, formed on the device; the copy to the host runs on its own stream
+// ---------------------------------------------------------------------------
+extern "C" int pm_export_begin(pm_solver* s) {
+  if (!s) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  const KP& k = s->kp;
+  auto& x = s->ex;
+  if (x.pending) return fail(s, PM_ERR_INVALID_ARGUMENT, "pm_export_begin: the previous export has not been collected with pm_export_wait");
+  const size_t n = size_t(k.nx) * size_t(k.nyl);
+  if (!x.dev) {
+    CK(cudaMalloc(&x.dev, 5 * n * sizeof(double)));
+    CK(cudaMallocHost(&x.host, 5 * n * sizeof(double)));
+    CK(cudaStreamCreateWithFlags(&x.stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&x.ready, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&x.done, cudaEventDisableTiming));
+  }
+  // the vorticity reads the cell centres one row up and down: one halo row of u and of v
+  PMTRY(exchange_halo1(s, s->pl[PL_U]));
+  PMTRY(exchange_halo1(s, s->pl[PL_V]));
+  const int psplit = s->use_tiled && s->p_split && !s->p_nat;
+  const double* p = psplit ? s->tp[s->tp_cur] : s->pl[s->p_cur];
+  k_export<<<cell_grid(k), cell_block(), 0, s->stream>>>(k, s->pl[PL_U], s->pl[PL_V], p, psplit, s->mask, x.dev, n);
+  CKL(s);
+  CK(cudaEventRecord(x.ready, s->stream));
+  CK(cudaStreamWaitEvent(x.stream, x.ready, 0));
+  CK(cudaMemcpyAsync(x.host, x.dev, 5 * n * sizeof(double), cudaMemcpyDeviceToHost, x.stream));
+  CK(cudaEventRecord(x.done, x.stream));
+  x.pending = true;
+  return PM_OK;
+}
+
+extern "C" int pm_export_wait(pm_solver* s, double* uc, double* vc, double* mag, double* p, double* vort, size_t count) {
+  if (!s || !uc || !vc || !mag || !p || !vort) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  const KP& k = s->kp;
+  auto& x = s->ex;
+  if (!x.pending) return fail(s, PM_ERR_INVALID_ARGUMENT, "pm_export_wait without pm_export_begin");
+  if (count != size_t(k.nx) * size_t(k.ny)) return fail(s, PM_ERR_INVALID_ARGUMENT, "pm_export_wait: count %zu != nx*ny", count);
+  CK(cudaEventSynchronize(x.done));
+  x.pending = false;
+  const size_t n = size_t(k.nx) * size_t(k.nyl), off = size_t(k.j0) * size_t(k.nx);
+  double* dst[5] = {uc, vc, mag, p, vort};
+  for (int q = 0; q < 5; ++q) std::memcpy(dst[q] + off, x.host + size_t(q) * n, n * sizeof(double));
   return PM_OK;
 }
 

@@ -647,6 +647,61 @@ __global__ void __launch_bounds__(PM_BX* PM_BY)
   const double s = block_sum(ke, sh);
   if (threadIdx.x == 0 && threadIdx.y == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
 }
+// Export-ready fields of the VTK writers, one dense row-major array of nyl x nx doubles each (this rank's rows):
+// interpolateToCellCenters (cavity-01.cpp:717-733; channel-01.cpp:708-731; backwards_step-01.cpp:981-1009: solid cells stay 0),
+// the magnitude sqrt(uc*uc + vc*vc) and the vorticity loops of the writers with their own expression trees
+// (cavity-01.cpp:187-223: (diff * dx_inv) * 0.5 inside, one-sided at the edges; channel-01.cpp:171-182: (0.5 * diff) * idx;
+// backwards_step-01.cpp:203-236: only where the cell and its four neighbours are fluid and off the domain edge, else 0).
+// Every operation individually rounded, like the host code it replaces (-ffp-contract=off).  p: natural plane or split-row buffer.
+__global__ void __launch_bounds__(PM_BX* PM_BY)
+    k_export(const __grid_constant__ KP k, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ p, int psplit,
+             const uint8_t* __restrict__ M, double* __restrict__ out, size_t field_stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > k.nx || jl > k.nyl) return;
+  const int P = k.pitch, j = k.j0 + jl;
+  const size_t c = pm_idx(k, jl, i);
+  const bool mask = k.has_mask != 0;
+  auto fluid = [&](size_t q) { return !mask || M[q] != 0; };
+  auto ucen = [&](size_t q) { return fluid(q) ? __dmul_rn(0.5, __dadd_rn(u[q - 1], u[q])) : 0.0; };
+  auto vcen = [&](size_t q) { return fluid(q) ? __dmul_rn(0.5, __dadd_rn(v[q - P], v[q])) : 0.0; };
+  const bool fl = fluid(c);
+  const double uc = ucen(c), vc = vcen(c);
+  double vort = 0.0;
+  if (k.case_id == PM_CASE_CAVITY) {
+    double dvdx, dudy;
+    if (i == 1) dvdx = __dmul_rn(__dsub_rn(vcen(c + 1), vc), k.idx);
+    else if (i == k.nx) dvdx = __dmul_rn(__dsub_rn(vc, vcen(c - 1)), k.idx);
+    else dvdx = __dmul_rn(__dmul_rn(__dsub_rn(vcen(c + 1), vcen(c - 1)), k.idx), 0.5);
+    if (j == 1) dudy = __dmul_rn(__dsub_rn(ucen(c + P), uc), k.idx);
+    else if (j == k.ny) dudy = __dmul_rn(__dsub_rn(uc, ucen(c - P)), k.idx);
+    else dudy = __dmul_rn(__dmul_rn(__dsub_rn(ucen(c + P), ucen(c - P)), k.idx), 0.5);
+    vort = __dsub_rn(dvdx, dudy);
+  } else if (k.case_id == PM_CASE_CHANNEL) {
+    double dvdx, dudy;
+    if (i == 1) dvdx = __dmul_rn(__dsub_rn(vcen(c + 1), vc), k.idx);
+    else if (i == k.nx) dvdx = __dmul_rn(__dsub_rn(vc, vcen(c - 1)), k.idx);
+    else dvdx = __dmul_rn(__dmul_rn(0.5, __dsub_rn(vcen(c + 1), vcen(c - 1))), k.idx);
+    if (j == 1) dudy = __dmul_rn(__dsub_rn(ucen(c + P), uc), k.idy);
+    else if (j == k.ny) dudy = __dmul_rn(__dsub_rn(uc, ucen(c - P)), k.idy);
+    else dudy = __dmul_rn(__dmul_rn(0.5, __dsub_rn(ucen(c + P), ucen(c - P))), k.idy);
+    vort = __dsub_rn(dvdx, dudy);
+  } else {
+    const bool ok = fl && !(i == 1 || i == k.nx || j == 1 || j == k.ny) && M[c - 1] && M[c + 1] && M[c - P] && M[c + P];
+    if (ok) {
+      const double dvdx = __dmul_rn(__dmul_rn(0.5, __dsub_rn(vcen(c + 1), vcen(c - 1))), k.idx);
+      const double dudy = __dmul_rn(__dmul_rn(0.5, __dsub_rn(ucen(c + P), ucen(c - P))), k.idy);
+      vort = __dsub_rn(dvdx, dudy);
+    }
+  }
+  const size_t o = size_t(jl - 1) * size_t(k.nx) + size_t(i - 1);
+  out[o] = uc;
+  out[o + field_stride] = vc;
+  out[o + 2 * field_stride] = fl ? __dsqrt_rn(__dadd_rn(__dmul_rn(uc, uc), __dmul_rn(vc, vc))) : 0.0;
+  out[o + 3 * field_stride] = fl ? p[psplit ? pm_sidx(k, jl, i) : c] : 0.0;
+  out[o + 4 * field_stride] = vort;
+}
+
 __global__ void k_sum_partials(const double* __restrict__ partial, int n, PpeState* __restrict__ st) {
   __shared__ double sh[32];
   double s = 0.0;

@@ -62,7 +62,7 @@ EXPORTS = [
     "pm_config_init", "pm_slab_range", "pm_cheby_omega", "pm_omega_mixed_bc", "pm_stream_plan", "pm_create", "pm_destroy", "pm_last_error", "pm_status_string",
     "pm_abi_version", "pm_nccl_unique_id", "pm_upload", "pm_download", "pm_slab_rows", "pm_upload_slab", "pm_download_slab", "pm_upload_mask", "pm_download_mask",
     "pm_fill_random", "pm_fill_random_scaled", "pm_fill_zero", "pm_apply_bc", "pm_predict", "pm_source", "pm_ppe_solve", "pm_correct",
-    "pm_step", "pm_host_step_submit", "pm_host_step_run", "pm_host_step_drain", "pm_diagnostics", "pm_sync", "pm_get_timing", "pm_timer_start", "pm_timer_stop",
+    "pm_step", "pm_host_step_submit", "pm_host_step_run", "pm_host_step_drain", "pm_diagnostics", "pm_export_begin", "pm_export_wait", "pm_sync", "pm_get_timing", "pm_timer_start", "pm_timer_stop",
 ]
 
 _lib = None
@@ -84,6 +84,8 @@ def lib():
     L.pm_cheby_omega.argtypes = [C.c_double, C.c_int]; L.pm_cheby_omega.restype = C.c_double
     L.pm_omega_mixed_bc.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]; L.pm_omega_mixed_bc.restype = C.c_double
     L.pm_stream_plan.argtypes = [C.c_int] * 7 + [C.POINTER(C.c_int)]
+    L.pm_export_begin.argtypes = [vp]
+    L.pm_export_wait.argtypes = [vp, dp, dp, dp, dp, dp, C.c_size_t]
     L.pm_create.argtypes = [C.POINTER(PmConfig), C.POINTER(vp)]
     L.pm_destroy.argtypes = [vp]
     L.pm_last_error.argtypes = [vp]; L.pm_last_error.restype = C.c_char_p
@@ -206,6 +208,17 @@ class Solver:
         a, b = C.c_double(), C.c_double()
         self._ck(lib().pm_diagnostics(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def export_begin(self):
+        self._ck(lib().pm_export_begin(self._h))
+
+    def export_wait(self, out=None):
+        """u_center, v_center, magnitude, pressure, vorticity as (ny, nx) arrays (this rank's rows filled)."""
+        nx, ny = self.cfg.nx, self.cfg.ny
+        out = out if out is not None else [np.zeros((ny, nx)) for _ in range(5)]
+        ptrs = [a.ctypes.data_as(C.POINTER(C.c_double)) for a in out]
+        self._ck(lib().pm_export_wait(self._h, *ptrs, nx * ny))
+        return out
 
     def sync(self):
         self._ck(lib().pm_sync(self._h))

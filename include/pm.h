@@ -229,6 +229,15 @@ int pm_host_step_drain(pm_solver* s);
  * velocity (logStatistics, cavity-01.cpp:741-766). */
 int pm_diagnostics(pm_solver* s, double* max_div, double* avg_ke);
 
+/* What the VTK writers print, formed on the device (interpolateToCellCenters and the vorticity loops: cavity-01.cpp:717-733,
+ * 187-223; channel-01.cpp:708-731,171-182; backwards_step-01.cpp:981-1009,203-236), bit for bit what the host loops give:
+ * five dense row-major arrays of ny x nx doubles (j = 1..ny, i = 1..nx) -- u_center, v_center, velocity magnitude, pressure,
+ * vorticity; solid cells (step) and vorticity cells the step writer skips hold 0.  pm_export_begin enqueues the kernel behind
+ * the current state and starts the copy to pinned host memory on its own stream, so time steps issued afterwards overlap it;
+ * pm_export_wait waits for the copy and fills this rank's rows of the caller's arrays (count = nx * ny each). */
+int pm_export_begin(pm_solver* s);
+int pm_export_wait(pm_solver* s, double* u_center, double* v_center, double* magnitude, double* pressure, double* vorticity, size_t count);
+
 /* Block until all work queued on the handle has finished. */
 int pm_sync(pm_solver* s);
 
