@@ -312,6 +312,7 @@ struct Run {
     const bool root = rank == 0;
     Snapshot& sn0 = shared ? *shared : snap;
     if (root) sn0.fluid.assign(size_t(cfg.ny + 2) * (cfg.nx + 2), 0);
+    if (opt.vtk) check(pm_export_prepare(s), s, "export buffers");  // before any rank's first collective (see pm.h)
     sync_ranks();
     check(pm_download_mask(s, sn0.fluid.data(), sn0.fluid.size()), s, "mask");  // each rank fills its rows
     sync_ranks();

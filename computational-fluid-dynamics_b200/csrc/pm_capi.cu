@@ -391,7 +391,9 @@ static int create_impl(pm_solver* s, const pm_config* cfg) {
   s->no_cluster = std::getenv("PM_NO_CLUSTER") != nullptr;
   s->use_small = small_ok && (c.kernel_path == PM_PATH_PERSISTENT || c.kernel_path == PM_PATH_AUTO);
   s->use_tiled = tiled_ok && !s->use_small && c.ppe_method != PM_PPE_SOR_LEX &&
-                 (c.kernel_path == PM_PATH_TILED || (c.kernel_path == PM_PATH_AUTO && (c.nranks == 1 || nyl >= 2 * PM_PADR)));
+                 (c.kernel_path == PM_PATH_TILED || (c.kernel_path == PM_PATH_AUTO && (c.nranks == 1 || c.ny / c.nranks >= 2 * PM_PADR)));
+  // (the slab test looks at the smallest slab of the decomposition, not at this rank's: every rank must take the same path,
+  // or their NCCL call sequences differ -- 31 rows on 2 ranks are 16 + 15)
   if (s->use_tiled) {
     std::string e;
     CK(cudaMalloc(&s->tp[0], s->plane * 2 * sizeof(double)));
@@ -1574,6 +1576,23 @@ extern "C" int pm_diagnostics(pm_solver* s, double* max_div, double* avg_ke) {
 // ---------------------------------------------------------------------------
 // export: what the VTK writers print, formed on the device; the copy to the host runs on its own stream
 // ---------------------------------------------------------------------------
+// The staging buffers.  Allocation synchronises devices, so with several handles driven by threads of ONE process it must
+// not run while another handle's NCCL kernel waits for this one's (the classic cudaMalloc / NCCL deadlock): such callers
+// prepare every handle up front, behind a barrier; everyone else gets it lazily from pm_export_begin.
+extern "C" int pm_export_prepare(pm_solver* s) {
+  if (!s) return PM_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  auto& x = s->ex;
+  if (x.dev) return PM_OK;
+  const size_t n = size_t(s->kp.nx) * size_t(s->kp.nyl);
+  CK(cudaMalloc(&x.dev, 5 * n * sizeof(double)));
+  CK(cudaMallocHost(&x.host, 5 * n * sizeof(double)));
+  CK(cudaStreamCreateWithFlags(&x.stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&x.ready, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&x.done, cudaEventDisableTiming));
+  return PM_OK;
+}
+
 extern "C" int pm_export_begin(pm_solver* s) {
   if (!s) return PM_ERR_INVALID_ARGUMENT;
   CK(cudaSetDevice(s->device));
@@ -1581,13 +1600,7 @@ extern "C" int pm_export_begin(pm_solver* s) {
   auto& x = s->ex;
   if (x.pending) return fail(s, PM_ERR_INVALID_ARGUMENT, "pm_export_begin: the previous export has not been collected with pm_export_wait");
   const size_t n = size_t(k.nx) * size_t(k.nyl);
-  if (!x.dev) {
-    CK(cudaMalloc(&x.dev, 5 * n * sizeof(double)));
-    CK(cudaMallocHost(&x.host, 5 * n * sizeof(double)));
-    CK(cudaStreamCreateWithFlags(&x.stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&x.ready, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&x.done, cudaEventDisableTiming));
-  }
+  PMTRY(pm_export_prepare(s));
   // the vorticity reads the cell centres one row up and down: one halo row of u and of v
   PMTRY(exchange_halo1(s, s->pl[PL_U]));
   PMTRY(exchange_halo1(s, s->pl[PL_V]));

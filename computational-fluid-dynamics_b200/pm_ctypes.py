@@ -62,7 +62,7 @@ EXPORTS = [
     "pm_config_init", "pm_slab_range", "pm_cheby_omega", "pm_omega_mixed_bc", "pm_stream_plan", "pm_create", "pm_destroy", "pm_last_error", "pm_status_string",
     "pm_abi_version", "pm_nccl_unique_id", "pm_upload", "pm_download", "pm_slab_rows", "pm_upload_slab", "pm_download_slab", "pm_upload_mask", "pm_download_mask",
     "pm_fill_random", "pm_fill_random_scaled", "pm_fill_zero", "pm_apply_bc", "pm_predict", "pm_source", "pm_ppe_solve", "pm_correct",
-    "pm_step", "pm_host_step_submit", "pm_host_step_run", "pm_host_step_drain", "pm_diagnostics", "pm_export_begin", "pm_export_wait", "pm_sync", "pm_get_timing", "pm_timer_start", "pm_timer_stop",
+    "pm_step", "pm_host_step_submit", "pm_host_step_run", "pm_host_step_drain", "pm_diagnostics", "pm_export_prepare", "pm_export_begin", "pm_export_wait", "pm_sync", "pm_get_timing", "pm_timer_start", "pm_timer_stop",
 ]
 
 _lib = None
@@ -84,6 +84,7 @@ def lib():
     L.pm_cheby_omega.argtypes = [C.c_double, C.c_int]; L.pm_cheby_omega.restype = C.c_double
     L.pm_omega_mixed_bc.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]; L.pm_omega_mixed_bc.restype = C.c_double
     L.pm_stream_plan.argtypes = [C.c_int] * 7 + [C.POINTER(C.c_int)]
+    L.pm_export_prepare.argtypes = [vp]
     L.pm_export_begin.argtypes = [vp]
     L.pm_export_wait.argtypes = [vp, dp, dp, dp, dp, dp, C.c_size_t]
     L.pm_create.argtypes = [C.POINTER(PmConfig), C.POINTER(vp)]

@@ -235,6 +235,9 @@ int pm_diagnostics(pm_solver* s, double* max_div, double* avg_ke);
  * vorticity; solid cells (step) and vorticity cells the step writer skips hold 0.  pm_export_begin enqueues the kernel behind
  * the current state and starts the copy to pinned host memory on its own stream, so time steps issued afterwards overlap it;
  * pm_export_wait waits for the copy and fills this rank's rows of the caller's arrays (count = nx * ny each). */
+int pm_export_prepare(pm_solver* s); /* allocate the staging buffers now (pm_export_begin does it lazily).  Needed only when one
+                                       * process drives several handles from threads: allocation synchronises devices and must
+                                       * not race another handle's NCCL call, so prepare all handles first, then a barrier */
 int pm_export_begin(pm_solver* s);
 int pm_export_wait(pm_solver* s, double* u_center, double* v_center, double* magnitude, double* pressure, double* vorticity, size_t count);
 

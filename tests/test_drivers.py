@@ -87,3 +87,22 @@ def test_production_ordering_prints_the_reference_diagnostics(tmp_path):
     assert len(ours) == 3
     for a, b in zip(ours, ref):
         assert a.split("| SOR_iters")[0] == b.split("| SOR_iters")[0]
+
+
+@pytest.mark.parametrize("exe", ["channel", "backwards_step"])
+def test_two_gpu_driver_writes_the_single_gpu_frames(tmp_path, exe):
+    """bin/<case> --gpus 2 (one host thread and one handle per GPU, NCCL between them) against --gpus 1 with exact arithmetic:
+    the same VTK bytes.  The default channel (31 rows -> slabs of 16 + 15) is the case where the kernel path once depended on
+    the rank's own slab height and the ranks' collective sequences diverged."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    args = ["--steps", "6", "--save-interval", "2", "--max-iters", "40", "--exact", "1"]
+    d1, d2 = tmp_path / "one", tmp_path / "two"
+    rc1, _, err1 = run(exe, args + ["--outdir", str(d1)], tmp_path)
+    rc2, _, err2 = run(exe, args + ["--gpus", "2", "--outdir", str(d2)], tmp_path)
+    assert rc1 == 0 and rc2 == 0, (err1, err2)
+    names = sorted(os.listdir(d1))
+    assert names == sorted(os.listdir(d2)) and len(names) >= 4
+    for n in names:
+        assert md5(d1 / n) == md5(d2 / n), n
