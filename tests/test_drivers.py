@@ -19,8 +19,8 @@ ANSI = re.compile(r"\x1b\[[0-9;]*m")
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "drivers.json")))
 
 
-def run(exe, args, cwd):
-    p = subprocess.run([os.path.join(BIN, exe)] + args, cwd=cwd, capture_output=True, text=True, timeout=600)
+def run(exe, args, cwd, timeout=600):
+    p = subprocess.run([os.path.join(BIN, exe)] + args, cwd=cwd, capture_output=True, text=True, timeout=timeout)
     return p.returncode, ANSI.sub("", p.stdout).splitlines(), ANSI.sub("", p.stderr).splitlines()
 
 
@@ -99,8 +99,8 @@ def test_two_gpu_driver_writes_the_single_gpu_frames(tmp_path, exe):
         pytest.skip("needs >= 2 GPUs")
     args = ["--steps", "6", "--save-interval", "2", "--max-iters", "40", "--exact", "1"]
     d1, d2 = tmp_path / "one", tmp_path / "two"
-    rc1, _, err1 = run(exe, args + ["--outdir", str(d1)], tmp_path)
-    rc2, _, err2 = run(exe, args + ["--gpus", "2", "--outdir", str(d2)], tmp_path)
+    rc1, _, err1 = run(exe, args + ["--outdir", str(d1)], tmp_path, timeout=90)
+    rc2, _, err2 = run(exe, args + ["--gpus", "2", "--outdir", str(d2)], tmp_path, timeout=90)
     assert rc1 == 0 and rc2 == 0, (err1, err2)
     names = sorted(os.listdir(d1))
     assert names == sorted(os.listdir(d2)) and len(names) >= 4
