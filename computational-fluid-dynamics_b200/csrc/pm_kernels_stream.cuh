@@ -257,7 +257,9 @@ __global__ void __launch_bounds__(32, PM_STREAM_MINB)
   }
 #pragma unroll 1
   for (;;) {
+    __syncwarp();  // every lane writes the same words; all lanes have read a word before any lane overwrites it
     const int it = loopc[0], nit = loopc[1], it_steady_last = loopc[2];
+    __syncwarp();
     if (it >= nit) break;
     loopc[0] = it + 1;
     if (it >= 2 && it <= it_steady_last) {
