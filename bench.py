@@ -238,6 +238,16 @@ def secondary_lines(pm, args, local):
                                     "ms_per_step": ms, "value": nx * ny / ms / 1e3, "unit": UNIT, "iterations": r.iterations,
                                     "algorithmic_GBps": bytes_per_cell_step(K_ITERS) * nx * ny / ms / 1e6,
                                     "launches_per_step": (t1.kernel_launches - t0.kernel_launches) / 8}
+    # the weak-scaling slab (BASELINE configs[4]: 16384^2 per GPU) on this one GPU
+    if not args.n:
+        n2 = 16384
+        cfg = bench_cfg(pm, "cavity", n2, n2, K_ITERS, args, local)
+        S = pm.Solver(cfg)
+        init_state(S, "cavity")
+        ms, r = device_timed(S, 4, 2)
+        S.close()
+        out[f"cavity_{n2}x{n2}"] = {"workload": f"cavity {n2}x{n2}, K={K_ITERS} (one slab of the N > 1 runs)", "ms_per_step": ms, "value": n2 * n2 / ms / 1e3,
+                                    "unit": UNIT, "iterations": r.iterations, "algorithmic_GBps": bytes_per_cell_step(K_ITERS) * n2 * n2 / ms / 1e6}
     return out
 
 
