@@ -18,6 +18,7 @@
 #include "pm_kernels_simple.cuh"
 #include "pm_kernels_tiled.cuh"
 #include "pm_kernels_stream.cuh"
+#include "pm_kernels_residual.cuh"
 #include "pm_kernels_lex.cuh"
 #include "pm_nccl.hpp"
 
@@ -994,6 +995,19 @@ static int tiled_pass(pm_solver* s, int in, int m0, int nsw, int force) {
   // A full pass of production red-black: the interior tiles go to the streaming kernel, the frame around them (tiles at a
   // wall) to k_ppe_tiled on the high-priority stream, both at once.
   const bool streamed = sp.on && nsw == pl.sweeps;
+  if (nsw == 0 && sp.on && std::getenv("PM_NO_RESIDUAL_ROWS") == nullptr) {
+    // the residual-only pass behind a capped solve: one row-wise look at p and f (pm_kernels_residual.cuh), bit-identical to
+    // k_ppe_tiled with nsw = 0; nothing is written, so no halo travels
+    const dim3 b(128, 4), g((((k.nx + 1) / 2) + 127) / 128, (k.nyl + 3) / 4);
+    if (k.case_id == PM_CASE_CAVITY) k_residual_split<0><<<g, b, 0, s->stream>>>(k, pl.p[in], f, s->d_state, s->d_res, pl.fold_part, m0, force);
+    else k_residual_split<1><<<g, b, 0, s->stream>>>(k, pl.p[in], f, s->d_state, s->d_res, pl.fold_part, m0, force);
+    CKL(s);
+    CK(tiled_fold_launch(&pl, k, s->d_res, m0, nsw, s->stream));
+    s->timing.kernel_launches += 2;
+    if (s->cfg.nranks > 1 && !force && m0 >= 1) PMTRY(allreduce_res(s, m0, 1));
+    s->timing.ppe_passes++;
+    return PM_OK;
+  }
   int bot = 0, top = 0;
   slab_edge_rows(s, &bot, &top);
   if (s->cfg.nranks == 1 || bot + top >= pl.tiles_y) {
