@@ -148,3 +148,42 @@ def test_omega_of_the_mixed_bc_operator_and_cheby(pm, orc, case_id, nx, ny, gain
     if not r_ref.hit_cap:
         scale = np.abs(p_ref).max()
         assert np.abs(p_mix - p_ref).max() <= 1e-4 * scale and np.abs(p_chb - p_ref).max() <= 1e-4 * scale  # both stop at the same residual tolerance
+
+
+def _jacobi_matrix(case_id, nx, ny, dx, dy):
+    """Jacobi iteration matrix D^-1 (L + U) of the operator the reference's sweeps relax (cavity-01.cpp:644-654: eps = 0 at the west,
+    east and north walls, the south ghost row is data; channel-01.cpp:531-541,659-666: mirror ghosts west / south / north, 0 east)."""
+    n = nx * ny
+    A = np.zeros((n, n))
+    idx = lambda j, i: (j - 1) * nx + (i - 1)
+    ix2, iy2 = 1.0 / (dx * dx), 1.0 / (dy * dy)
+    for j in range(1, ny + 1):
+        for i in range(1, nx + 1):
+            r = idx(j, i)
+            if case_id == 0:
+                nb = [(j, i - 1, i > 1), (j, i + 1, i < nx), (j + 1, i, j < ny), (j - 1, i, True)]
+                nc = sum(1 for *_, on in nb if on)
+                for jj, ii, on in nb:
+                    if on and 1 <= jj <= ny:  # (the south ghost row is constant: no entry)
+                        A[r, idx(jj, ii)] = 1.0 / nc
+            else:
+                denom = 2.0 * (ix2 + iy2)
+                for jj, ii, w in ((j, i - 1, ix2), (j, i + 1, ix2), (j + 1, i, iy2), (j - 1, i, iy2)):
+                    if ii > nx:
+                        continue              # outlet ghost column: 0
+                    ii, jj = max(ii, 1), min(max(jj, 1), ny)  # mirror ghosts read the wall-adjacent cell itself
+                    A[r, idx(jj, ii)] += w / denom
+    return A
+
+
+@pytest.mark.parametrize("case_id,nx,ny", [(0, 12, 12), (0, 20, 20), (1, 24, 8), (1, 32, 12)])
+def test_omega_mixed_bc_tracks_the_operators_spectral_radius(pm, orc, case_id, nx, ny):
+    """The Jacobi spectral radius behind pm_omega_mixed_bc against the true one of the iteration matrix (dense eigenvalues):
+    1 - rho agrees within 15 %, where the reference's Dirichlet-problem radius is off by a factor of 3 to 8 in 1 - rho."""
+    cfg = orc.config_init(case_id, nx, ny)
+    rho_true = np.abs(np.linalg.eigvals(_jacobi_matrix(case_id, nx, ny, cfg.dx, cfg.dy))).max()
+    w = pm.lib().pm_omega_mixed_bc(case_id, nx, ny, cfg.dx, cfg.dy)
+    rho_mixed = np.sqrt(1.0 - (2.0 / w - 1.0) ** 2)
+    rho_ref = np.sqrt(1.0 - (2.0 / cfg.omega - 1.0) ** 2)
+    assert abs((1 - rho_mixed) - (1 - rho_true)) <= 0.15 * (1 - rho_true), (rho_true, rho_mixed)
+    assert (1 - rho_ref) >= 3.0 * (1 - rho_true), (rho_true, rho_ref)
