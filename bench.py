@@ -550,7 +550,7 @@ def run_ours(args):
             cfg1 = bench_cfg(pm, case, nx, ny_local, K_ITERS, args, local)
             S1 = pm.Solver(cfg1)
             init_state(S1, case)
-            b_ms, _ = device_timed(S1, max(3, min(args.steps, 8)), 3)
+            b_ms, _ = device_timed(S1, max(3, min(args.steps, 20)), max(3, args.warmup))  # as many steps as the run it is the base of (power state)
             S1.close()
             weak_base = {"workload": f"{case} {nx}x{ny_local} on 1 GPU (one slab of the above), same K, same kernel", "ms_per_step": b_ms,
                          "value": nx * ny_local / b_ms / 1e3, "unit": UNIT,
